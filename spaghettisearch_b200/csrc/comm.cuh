@@ -1,0 +1,14 @@
+// Cross-GPU exchange used by the sharded paths; no-ops for
+// world == 1.  All calls enqueue on the engine stream.
+#pragma once
+#include <stddef.h>
+
+#include "spaghetti.h"
+
+int comm_rank(const ss_engine* e);
+int comm_world(const ss_engine* e);
+// in-place sum over ranks of a small device vector (normaliser / residual)
+int comm_allreduce_sum_f64(ss_engine* e, double* dev_buf, size_t count);
+// every rank r contributes dev_buf[byte_off[r] .. +byte_cnt[r]) of a buffer that
+// has the same layout on all ranks (rank blocks of the PageRank state)
+int comm_allgatherv_bytes(ss_engine* e, void* dev_buf, const size_t* byte_off, const size_t* byte_cnt);

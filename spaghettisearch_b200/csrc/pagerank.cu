@@ -1,0 +1,868 @@
+// HP-1: the reference's "topic-sensitive" PageRank (ranking/pagerank.go:14-145)
+// as a pull SpMM over the in-edge lists, all topics advanced together.
+//
+// Reference update for one topic (pagerank.go:93-119), last = previous ranks:
+//   w_p      = d * last[p] / out(p)            for every parent with out(p) > 0
+//   inh[c]   = sum of w_p over in-edges p -> c  (+ 1/n in the very first sweep,
+//              because iteration 1 accumulates on top of the initial value)
+//   Tot      = sum_p w_p + (1-d) * N            (each parent counted ONCE)
+//   cur[v]   = (inh[v] + (1-d)) / Tot ;  delta = sum_v |cur[v] - last[v]|
+// There is no dangling-mass term and teleport is uniform for every topic; the
+// topic enters only through the start value 1/numPages[t].
+//
+// Device layout (per rank): the state is kept PRE-SCALED,
+//   y[v][t] = rank[v][t] * m(v),  m(v) = d/out(v) if out(v) > 0 else 1,
+// row major [N][TP] fp64 (TP = topics padded to 2/4/8/16; 128-byte rows at
+// T = 16), so that an in-edge gather is one aligned row load with no per-edge
+// scale and the normaliser is S_t = sum over non-dangling rows of y[.][t].
+// One sweep reads col-idx once, gathers E rows of y_last, streams y_last and
+// y_next once: the algorithmic bytes of SURVEY.md §8(d).
+//
+// Work split: rows with in-degree <= kShortMax are handled one per sub-warp
+// (LPR lanes, 16 bytes per lane); longer rows are cut into kChunk-edge tasks,
+// one warp each, ordered by first source id so that concurrently running tasks
+// gather from neighbouring source ranges (L2 reuse); rows spanning several
+// tasks are finished by a fix-up pass that sums their partial rows in task
+// order.  Every reduction has a fixed shape, so results are deterministic.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+#include "comm.cuh"
+#include "common.cuh"
+
+namespace {
+
+constexpr uint32_t kShortMax = 32;   // longest row handled by one sub-warp
+constexpr uint32_t kChunk = 512;     // edges per long-row task
+constexpr int kThreads = 256;
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+struct LongTask {
+  uint64_t e_begin;  // offset into in_src
+  uint32_t row;      // local destination row
+  uint32_t n;        // edges in this task
+  int32_t slot;      // partial-row slot, or -1 when the task covers the whole row
+  uint32_t pad;
+};
+struct FixRow {
+  uint32_t row, first_slot, n_slots, pad;
+};
+
+struct SweepParams {
+  const double* y_last;
+  double* y_next;
+  const uint64_t* in_ptr;   // [rows_loc + 1], offsets into in_src
+  const uint32_t* in_src;   // sources ascending within a row
+  const double* mul;        // [rows_loc] d/out, or 0 for dangling rows
+  const double* tot;        // [TP] S_t + (1-d) N
+  const double* init;       // [TP] 1/num_pages[t]
+  double* red;              // [slots][3*TP] per-CTA partial sums (delta, S, changed)
+  uint64_t row_lo;          // global id of local row 0
+  uint32_t rows_loc;
+  uint32_t active_mask;     // bit t set: topic t still iterating
+  double tele;              // 1 - d
+  int first;                // sweep 1: add 1/n, compare against 1/n
+};
+
+__device__ __forceinline__ double2 ld_row_gather(const double* p) {
+  return __ldg(reinterpret_cast<const double2*>(p));
+}
+__device__ __forceinline__ double2 ld_row_stream(const double* p) {
+  return __ldcs(reinterpret_cast<const double2*>(p));
+}
+__device__ __forceinline__ void st_row_stream(double* p, double2 v) {
+  __stcs(reinterpret_cast<double2*>(p), v);
+}
+
+struct Acc {  // per-thread running sums for its two topic columns
+  double d0 = 0, d1 = 0, s0 = 0, s1 = 0, c0 = 0, c1 = 0;
+};
+
+// Fused normalise / teleport / residual for one finished row; executed by the
+// LPR lanes that own the row, lane l8 holding topics 2*l8 and 2*l8+1.
+template <int LPR>
+__device__ __forceinline__ void epilogue(const SweepParams& p, uint32_t r, int l8, double a0, double a1,
+                                         Acc& acc) {
+  constexpr int TP = 2 * LPR;
+  const uint64_t v = p.row_lo + r;
+  const double m = p.mul[r];
+  const bool has_out = m > 0.0;
+  const double mul = has_out ? m : 1.0;
+  const double2 yl = ld_row_stream(p.y_last + v * TP + 2 * l8);
+  double2 yn;
+  {
+    const int t = 2 * l8;
+    double last_rank = yl.x / mul;
+    if (p.first) {
+      a0 += p.init[t];
+      last_rank = p.init[t];
+    }
+    if ((p.active_mask >> t) & 1u) {
+      double nr = (a0 + p.tele) / p.tot[t];
+      acc.d0 += fabs(nr - last_rank);
+      yn.x = nr * mul;
+      acc.c0 += (__double_as_longlong(yn.x) != __double_as_longlong(yl.x)) ? 1.0 : 0.0;
+    } else {
+      yn.x = yl.x;
+    }
+    if (has_out) acc.s0 += yn.x;
+  }
+  {
+    const int t = 2 * l8 + 1;
+    double last_rank = yl.y / mul;
+    if (p.first) {
+      a1 += p.init[t];
+      last_rank = p.init[t];
+    }
+    if ((p.active_mask >> t) & 1u) {
+      double nr = (a1 + p.tele) / p.tot[t];
+      acc.d1 += fabs(nr - last_rank);
+      yn.y = nr * mul;
+      acc.c1 += (__double_as_longlong(yn.y) != __double_as_longlong(yl.y)) ? 1.0 : 0.0;
+    } else {
+      yn.y = yl.y;
+    }
+    if (has_out) acc.s1 += yn.y;
+  }
+  st_row_stream(p.y_next + v * TP + 2 * l8, yn);
+}
+
+// CTA-wide fixed-shape reduction of the per-thread sums into red[blockIdx.x].
+template <int LPR>
+__device__ __forceinline__ void block_reduce(const SweepParams& p, Acc acc, bool owner) {
+  constexpr int TP = 2 * LPR;
+  constexpr int kWarps = kThreads / 32;
+  __shared__ double sm[kWarps][3 * 16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l8 = lane % LPR;
+  double v[6] = {acc.d0, acc.d1, acc.s0, acc.s1, acc.c0, acc.c1};
+  if (!owner) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v[i] = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) v[i] += __shfl_xor_sync(0xFFFFFFFFu, v[i], o);
+  if (lane < LPR) {
+    sm[warp][2 * l8] = v[0];
+    sm[warp][2 * l8 + 1] = v[1];
+    sm[warp][TP + 2 * l8] = v[2];
+    sm[warp][TP + 2 * l8 + 1] = v[3];
+    sm[warp][2 * TP + 2 * l8] = v[4];
+    sm[warp][2 * TP + 2 * l8 + 1] = v[5];
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 * TP) {
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += sm[w][threadIdx.x];
+    p.red[(size_t)blockIdx.x * 3 * TP + threadIdx.x] = s;
+  }
+}
+
+// Rows with in-degree <= kShortMax: one row per LPR-lane group, 32/LPR rows
+// per warp, consecutive rows in consecutive groups (coalesced y rows).
+template <int LPR>
+__global__ void __launch_bounds__(kThreads) k_sweep_short(SweepParams p, uint32_t n_row_blocks) {
+  constexpr int TP = 2 * LPR, GPW = 32 / LPR, GPC = GPW * (kThreads / 32);
+  const int lane = threadIdx.x & 31, l8 = lane % LPR, g = lane / LPR;
+  const unsigned gmask = (LPR == 32 ? 0xFFFFFFFFu : ((1u << LPR) - 1u)) << (g * LPR);
+  const int group_in_cta = (threadIdx.x >> 5) * GPW + g;
+  Acc acc;
+  for (uint32_t rb = blockIdx.x; rb < n_row_blocks; rb += gridDim.x) {
+    const uint32_t r = rb * GPC + group_in_cta;
+    if (r >= p.rows_loc) continue;
+    const uint64_t b = p.in_ptr[r], e = p.in_ptr[r + 1];
+    if (e - b > kShortMax) continue;  // a long row: k_sweep_long / k_sweep_fix own it
+    double a0 = 0, a1 = 0;
+    for (uint64_t i = b; i < e; i += LPR) {
+      const uint32_t idx = (i + l8 < e) ? __ldg(p.in_src + i + l8) : kNone;
+#pragma unroll
+      for (int j = 0; j < LPR; ++j) {
+        const uint32_t u = __shfl_sync(gmask, idx, g * LPR + j);
+        if (u != kNone) {
+          const double2 row = ld_row_gather(p.y_last + (uint64_t)u * TP + 2 * l8);
+          a0 += row.x;
+          a1 += row.y;
+        }
+      }
+    }
+    epilogue<LPR>(p, r, l8, a0, a1, acc);
+  }
+  block_reduce<LPR>(p, acc, true);
+}
+
+// Long-row tasks: one warp per task, 32 edges per step, group g takes edges
+// j*GPW+g; the GPW partial rows are combined with shuffles.
+template <int LPR>
+__global__ void __launch_bounds__(kThreads) k_sweep_long(SweepParams p, const LongTask* __restrict__ tasks,
+                                                        uint32_t n_tasks, double* __restrict__ partials) {
+  constexpr int TP = 2 * LPR, GPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, l8 = lane % LPR, g = lane / LPR;
+  const uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * kThreads) >> 5;
+  Acc acc;
+  for (uint32_t ti = warp; ti < n_tasks; ti += n_warps) {
+    const LongTask t = tasks[ti];
+    const uint32_t* src = p.in_src + t.e_begin;
+    double a0 = 0, a1 = 0;
+    for (uint32_t i = 0; i < t.n; i += 32) {
+      const uint32_t idx = (i + lane < t.n) ? __ldg(src + i + lane) : kNone;
+#pragma unroll
+      for (int j = 0; j < LPR; ++j) {
+        const uint32_t u = __shfl_sync(0xFFFFFFFFu, idx, j * GPW + g);
+        if (u != kNone) {
+          const double2 row = ld_row_gather(p.y_last + (uint64_t)u * TP + 2 * l8);
+          a0 += row.x;
+          a1 += row.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+      a0 += __shfl_xor_sync(0xFFFFFFFFu, a0, o);
+      a1 += __shfl_xor_sync(0xFFFFFFFFu, a1, o);
+    }
+    if (g == 0) {
+      if (t.slot < 0) {
+        epilogue<LPR>(p, t.row, l8, a0, a1, acc);
+      } else {
+        *reinterpret_cast<double2*>(partials + (size_t)t.slot * TP + 2 * l8) = make_double2(a0, a1);
+      }
+    }
+  }
+  block_reduce<LPR>(p, acc, g == 0);
+}
+
+// Rows that span several tasks: one CTA per row sums the partial rows in slot
+// order (fixed tree) and runs the epilogue.
+template <int LPR>
+__global__ void __launch_bounds__(kThreads) k_sweep_fix(SweepParams p, const FixRow* __restrict__ rows,
+                                                       uint32_t n_fix, const double* __restrict__ partials) {
+  constexpr int TP = 2 * LPR, GPW = 32 / LPR, GPC = GPW * (kThreads / 32);
+  __shared__ double2 sm[kThreads / 32][LPR];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l8 = lane % LPR, g = lane / LPR;
+  const int group_in_cta = warp * GPW + g;
+  Acc acc;
+  for (uint32_t fi = blockIdx.x; fi < n_fix; fi += gridDim.x) {
+    const FixRow fr = rows[fi];
+    double a0 = 0, a1 = 0;
+    for (uint32_t s = group_in_cta; s < fr.n_slots; s += GPC) {
+      const double2 v = *reinterpret_cast<const double2*>(partials + (size_t)(fr.first_slot + s) * TP + 2 * l8);
+      a0 += v.x;
+      a1 += v.y;
+    }
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+      a0 += __shfl_xor_sync(0xFFFFFFFFu, a0, o);
+      a1 += __shfl_xor_sync(0xFFFFFFFFu, a1, o);
+    }
+    __syncthreads();  // sm reuse across iterations
+    if (g == 0) sm[warp][l8] = make_double2(a0, a1);
+    __syncthreads();
+    if (warp == 0 && g == 0) {
+      double b0 = 0, b1 = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) {
+        b0 += sm[w][l8].x;
+        b1 += sm[w][l8].y;
+      }
+      epilogue<LPR>(p, fr.row, l8, b0, b1, acc);
+    }
+  }
+  block_reduce<LPR>(p, acc, warp == 0 && g == 0);
+}
+
+// sums[0..width) = sum over all per-CTA partials, fixed stripe order (one CTA).
+constexpr int kReduceThreads = 1024;
+__global__ void __launch_bounds__(kReduceThreads) k_reduce_partials(const double* __restrict__ red, uint32_t n_slots,
+                                                                    int width, double* __restrict__ sums) {
+  __shared__ double sm[kReduceThreads];
+  const int stripes = kReduceThreads / width;
+  const int c = threadIdx.x % width, s = threadIdx.x / width;
+  double v = 0;
+  if (s < stripes) {
+#pragma unroll 8
+    for (uint32_t i = s; i < n_slots; i += stripes) v += red[(size_t)i * width + c];
+  }
+  sm[threadIdx.x] = (s < stripes) ? v : 0.0;
+  __syncthreads();
+  if (threadIdx.x < width) {
+    double t = 0;
+    for (int k = 0; k < stripes; ++k) t += sm[k * width + threadIdx.x];
+    sums[threadIdx.x] = t;
+  }
+}
+
+// tot[t] = S_t + (1-d) N  (pagerank.go:111-112), after the cross-rank sum.
+__global__ void k_finish_tot(const double* __restrict__ sums, int TP, double tele, double n_nodes,
+                             double* __restrict__ tot) {
+  const int t = threadIdx.x;
+  if (t < TP) tot[t] = sums[TP + t] + tele * n_nodes;
+}
+
+// y0[v][t] = m(v) / n_t for every node (pagerank.go:101-107) and the partial
+// S_0 of this rank's rows.
+template <int LPR>
+__global__ void __launch_bounds__(kThreads) k_init(double* __restrict__ y, const uint32_t* __restrict__ outdeg,
+                                                  uint64_t n_nodes, double damping, const double* __restrict__ init,
+                                                  uint64_t row_lo, uint32_t rows_loc, double* __restrict__ mul_loc,
+                                                  double* __restrict__ red) {
+  constexpr int TP = 2 * LPR;
+  __shared__ double sm[kThreads / 32][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l8 = lane % LPR;
+  const uint64_t n_groups = (uint64_t)gridDim.x * kThreads / LPR;
+  double s0 = 0, s1 = 0;
+  for (uint64_t v = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) / LPR; v < n_nodes; v += n_groups) {
+    const uint32_t od = outdeg[v];
+    const double m = od ? damping / (double)od : 1.0;
+    const double2 val = make_double2(m * init[2 * l8], m * init[2 * l8 + 1]);
+    *reinterpret_cast<double2*>(y + v * TP + 2 * l8) = val;
+    if (v >= row_lo && v < row_lo + rows_loc) {
+      if (l8 == 0) mul_loc[v - row_lo] = od ? m : 0.0;
+      if (od) {
+        s0 += val.x;
+        s1 += val.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = LPR; o < 32; o <<= 1) {
+    s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, o);
+    s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o);
+  }
+  if (lane < LPR) {
+    sm[warp][2 * l8] = s0;
+    sm[warp][2 * l8 + 1] = s1;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 * TP) {
+    double s = 0;
+    if (threadIdx.x >= TP && threadIdx.x < 2 * TP)
+      for (int w = 0; w < kThreads / 32; ++w) s += sm[w][threadIdx.x - TP];
+    red[(size_t)blockIdx.x * 3 * TP + threadIdx.x] = s;
+  }
+}
+
+// rank[v][t] = y[v][t] / m(v) for rows [lo, hi) into a dense [rows][T] buffer.
+__global__ void k_unscale(const double* __restrict__ y, const uint32_t* __restrict__ outdeg, double damping,
+                          int TP, int T, uint64_t lo, uint64_t hi, double* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t total = (hi - lo) * (uint64_t)T;
+  if (i >= total) return;
+  const uint64_t v = lo + i / T;
+  const int t = (int)(i % T);
+  const uint32_t od = outdeg[v];
+  const double m = od ? damping / (double)od : 1.0;
+  out[i] = y[v * TP + t] / m;
+}
+
+// ---- load-time kernels ------------------------------------------------------
+__global__ void k_outdeg(const uint64_t* __restrict__ row_ptr, uint64_t n, uint32_t* __restrict__ outdeg) {
+  const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < n) outdeg[u] = (uint32_t)(row_ptr[u + 1] - row_ptr[u]);
+}
+// src[e] = the row that owns out-edge e; in-degree histogram of the children.
+__global__ void k_expand_src(const uint64_t* __restrict__ row_ptr, uint64_t n, uint64_t n_edges,
+                             const uint32_t* __restrict__ col_idx, uint32_t* __restrict__ src,
+                             unsigned long long* __restrict__ indeg, int* __restrict__ bad) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  uint64_t lo = 0, hi = n;  // last u with row_ptr[u] <= e
+  while (hi - lo > 1) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (row_ptr[mid] <= e) lo = mid; else hi = mid;
+  }
+  src[e] = (uint32_t)lo;
+  const uint32_t c = col_idx[e];
+  if (c >= n) {
+    *bad = 1;
+    return;
+  }
+  atomicAdd(indeg + c + 1, 1ull);
+}
+__global__ void k_check_row_ptr(const uint64_t* __restrict__ row_ptr, uint64_t n, uint64_t n_edges,
+                                int* __restrict__ bad) {
+  const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < n && row_ptr[u] > row_ptr[u + 1]) *bad = 1;
+  if (u == 0 && (row_ptr[0] != 0 || row_ptr[n] != n_edges)) *bad = 1;
+}
+// Edge- and row-balanced 1-D partition: cost(v) = in_ptr[v] + 2 v is monotone;
+// boundary r = first v with cost(v) >= r * cost(N) / world.
+__global__ void k_partition(const unsigned long long* __restrict__ in_ptr, uint64_t n, int world,
+                            unsigned long long* __restrict__ bounds) {
+  const int r = threadIdx.x;
+  if (r > world) return;
+  if (r == world) {
+    bounds[r] = n;
+    return;
+  }
+  const unsigned long long total = in_ptr[n] + 2ull * n;
+  const unsigned long long want = (unsigned long long)(((unsigned __int128)total * (unsigned)r) / (unsigned)world);
+  uint64_t lo = 0, hi = n;  // first v with cost(v) >= want
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (in_ptr[mid] + 2ull * mid >= want) hi = mid; else lo = mid + 1;
+  }
+  bounds[r] = lo;
+}
+__global__ void k_local_ptr(const unsigned long long* __restrict__ in_ptr_full, uint64_t row_lo, uint32_t rows_loc,
+                            uint64_t* __restrict__ in_ptr_loc) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r <= rows_loc) in_ptr_loc[r] = in_ptr_full[row_lo + r] - in_ptr_full[row_lo];
+}
+__global__ void k_count_tasks(const uint64_t* __restrict__ in_ptr, uint32_t rows_loc, uint32_t* __restrict__ nt,
+                              uint32_t* __restrict__ nf) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows_loc) return;
+  const uint64_t deg = in_ptr[r + 1] - in_ptr[r];
+  const uint32_t t = deg > kShortMax ? (uint32_t)((deg + kChunk - 1) / kChunk) : 0u;
+  nt[r] = t;
+  nf[r] = t > 1 ? 1u : 0u;
+}
+__global__ void k_fill_tasks(const uint64_t* __restrict__ in_ptr, const uint32_t* __restrict__ in_src,
+                             uint32_t rows_loc, const uint32_t* __restrict__ nt, const uint32_t* __restrict__ toff,
+                             const uint32_t* __restrict__ foff, LongTask* __restrict__ tasks,
+                             uint32_t* __restrict__ keys, uint32_t* __restrict__ order, FixRow* __restrict__ fix) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows_loc) return;
+  const uint32_t t = nt[r];
+  if (t == 0) return;
+  const uint64_t b = in_ptr[r], deg = in_ptr[r + 1] - b;
+  const uint32_t base = toff[r];
+  for (uint32_t c = 0; c < t; ++c) {
+    LongTask k;
+    k.e_begin = b + (uint64_t)c * kChunk;
+    k.row = (uint32_t)r;
+    k.n = (uint32_t)min((uint64_t)kChunk, deg - (uint64_t)c * kChunk);
+    k.slot = t > 1 ? (int32_t)(base + c) : -1;
+    k.pad = 0;
+    tasks[base + c] = k;
+    keys[base + c] = in_src[k.e_begin];
+    order[base + c] = base + c;
+  }
+  if (t > 1) {
+    FixRow f;
+    f.row = (uint32_t)r;
+    f.first_slot = base;
+    f.n_slots = t;
+    f.pad = 0;
+    fix[foff[r]] = f;
+  }
+}
+__global__ void k_gather_tasks(const LongTask* __restrict__ in, const uint32_t* __restrict__ order, uint32_t n,
+                               LongTask* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[order[i]];
+}
+
+}  // namespace
+
+struct PagerankState {
+  uint64_t N = 0, E = 0;
+  uint64_t row_lo = 0;
+  uint32_t rows_loc = 0;
+  uint64_t E_loc = 0;
+  std::vector<uint64_t> bounds;  // [world + 1]
+  ss::DevBuf<uint32_t> outdeg;   // [N]
+  ss::DevBuf<uint64_t> in_ptr;   // [rows_loc + 1]
+  ss::DevBuf<uint32_t> in_src;   // [E_loc]
+  ss::DevBuf<LongTask> tasks;
+  ss::DevBuf<FixRow> fix;
+  uint32_t n_tasks = 0, n_fix = 0;
+  // per-run state
+  int TP = 0, T = 0;
+  double damping = 0;
+  ss::DevBuf<double> y[2];
+  int cur = 0;  // y[cur] holds the latest ranks
+  ss::DevBuf<double> mul, partials, red, sums, tot, init;
+  bool have_result = false;
+  ss_pagerank_stats stats{};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+void pagerank_state_free(PagerankState* s) {
+  if (!s) return;
+  for (auto& e : s->ev)
+    if (e) cudaEventDestroy(e);
+  delete s;
+}
+
+static int lpr_for_topics(uint32_t T) {
+  if (T <= 2) return 1;
+  if (T <= 4) return 2;
+  if (T <= 8) return 4;
+  return 8;
+}
+
+template <class F>
+static int dispatch_lpr(int lpr, F&& f) {
+  switch (lpr) {
+    case 1: return f(std::integral_constant<int, 1>());
+    case 2: return f(std::integral_constant<int, 2>());
+    case 4: return f(std::integral_constant<int, 4>());
+    default: return f(std::integral_constant<int, 8>());
+  }
+}
+
+extern "C" {
+
+SS_API int ss_graph_load_csr(ss_engine* e, uint64_t n_nodes, uint64_t n_edges, const uint64_t* row_ptr,
+                             const uint32_t* col_idx) {
+  SS_REQUIRE(e, SS_ERR_INVALID, "ss_graph_load_csr: engine is NULL");
+  SS_REQUIRE(row_ptr && (col_idx || n_edges == 0), SS_ERR_INVALID, "ss_graph_load_csr: NULL array");
+  SS_REQUIRE(n_nodes < 0xFFFFFFFFull, SS_ERR_INVALID, "ss_graph_load_csr: node ids are 32 bit");
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  auto t_begin = std::chrono::steady_clock::now();
+  pagerank_state_free(e->pr);
+  e->pr = nullptr;
+  PagerankState* s = new (std::nothrow) PagerankState();
+  SS_REQUIRE(s, SS_ERR_OOM, "host allocation failed");
+  struct Cleanup {
+    PagerankState*& s;
+    ~Cleanup() { if (s) pagerank_state_free(s); }
+  } cleanup{s};
+
+  cudaStream_t st = e->stream;
+  const uint64_t N = n_nodes, E = n_edges;
+  const int world = comm_world(e), rank = comm_rank(e);
+  s->N = N;
+  s->E = E;
+  s->bounds.assign(world + 1, 0);
+
+  ss::DevBuf<uint64_t> d_row_ptr;
+  ss::DevBuf<uint32_t> d_col, d_src, d_col_sorted, d_src_sorted;
+  ss::DevBuf<unsigned long long> d_in_ptr_full, d_bounds;
+  ss::DevBuf<int> d_bad;
+  SS_TRY(d_row_ptr.alloc(N + 1));
+  SS_TRY(d_col.alloc(E));
+  SS_TRY(d_src.alloc(E));
+  SS_TRY(d_in_ptr_full.alloc(N + 2));
+  SS_TRY(d_bounds.alloc(world + 1));
+  SS_TRY(d_bad.alloc(1));
+  SS_TRY(s->outdeg.alloc(N));
+  SS_CUDA(cudaMemcpyAsync(d_row_ptr.p, row_ptr, (N + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (E) SS_CUDA(cudaMemcpyAsync(d_col.p, col_idx, E * 4, cudaMemcpyHostToDevice, st));
+  SS_CUDA(cudaMemsetAsync(d_in_ptr_full.p, 0, (N + 2) * 8, st));
+  SS_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
+  if (N) {
+    k_check_row_ptr<<<ss::div_up(N, 256), 256, 0, st>>>(d_row_ptr.p, N, E, d_bad.p);
+    k_outdeg<<<ss::div_up(N, 256), 256, 0, st>>>(d_row_ptr.p, N, s->outdeg.p);
+  }
+  if (E) k_expand_src<<<ss::div_up(E, 256), 256, 0, st>>>(d_row_ptr.p, N, E, d_col.p, d_src.p, d_in_ptr_full.p, d_bad.p);
+  int bad = 0;
+  SS_CUDA(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaStreamSynchronize(st));
+  SS_REQUIRE(!bad, SS_ERR_INVALID, "ss_graph_load_csr: row_ptr not monotone / child id out of range");
+
+  // in_ptr_full = inclusive scan of the shifted histogram (slot v+1 holds indeg(v))
+  {
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, d_in_ptr_full.p, d_in_ptr_full.p, (int64_t)(N + 1), st);
+    ss::DevBuf<char> tmp;
+    SS_TRY(tmp.alloc(tmp_bytes));
+    SS_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, d_in_ptr_full.p, d_in_ptr_full.p, (int64_t)(N + 1), st));
+  }
+  SS_REQUIRE(world < 64, SS_ERR_INVALID, "world size %d too large", world);
+  k_partition<<<1, 64, 0, st>>>(d_in_ptr_full.p, N, world, d_bounds.p);
+  std::vector<unsigned long long> hb(world + 1);
+  SS_CUDA(cudaMemcpyAsync(hb.data(), d_bounds.p, (world + 1) * 8, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaStreamSynchronize(st));
+  for (int r = 0; r <= world; ++r) s->bounds[r] = hb[r];
+  s->row_lo = s->bounds[rank];
+  s->rows_loc = (uint32_t)(s->bounds[rank + 1] - s->bounds[rank]);
+
+  // sort edges by child (stable: parents stay ascending inside a row)
+  unsigned long long e_lo = 0, e_hi = 0;
+  SS_CUDA(cudaMemcpyAsync(&e_lo, d_in_ptr_full.p + s->row_lo, 8, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(&e_hi, d_in_ptr_full.p + s->row_lo + s->rows_loc, 8, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaStreamSynchronize(st));
+  s->E_loc = e_hi - e_lo;
+  SS_TRY(s->in_src.alloc(s->E_loc));
+  if (E) {
+    SS_TRY(d_col_sorted.alloc(E));
+    SS_TRY(d_src_sorted.alloc(E));
+    int end_bit = 1;
+    while ((1ull << end_bit) < N) ++end_bit;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_col.p, d_col_sorted.p, d_src.p, d_src_sorted.p,
+                                    (int64_t)E, 0, end_bit, st);
+    ss::DevBuf<char> tmp;
+    SS_TRY(tmp.alloc(tmp_bytes));
+    SS_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, d_col.p, d_col_sorted.p, d_src.p, d_src_sorted.p,
+                                            (int64_t)E, 0, end_bit, st));
+    if (s->E_loc)
+      SS_CUDA(cudaMemcpyAsync(s->in_src.p, d_src_sorted.p + e_lo, s->E_loc * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  SS_TRY(s->in_ptr.alloc((size_t)s->rows_loc + 1));
+  k_local_ptr<<<ss::div_up((uint64_t)s->rows_loc + 1, 256), 256, 0, st>>>(d_in_ptr_full.p, s->row_lo, s->rows_loc,
+                                                                         s->in_ptr.p);
+  SS_CUDA(cudaStreamSynchronize(st));
+  d_col.reset();
+  d_src.reset();
+  d_col_sorted.reset();
+  d_src_sorted.reset();
+  d_row_ptr.reset();
+
+  // long-row tasks and fix rows
+  if (s->rows_loc) {
+    const uint32_t R = s->rows_loc;
+    ss::DevBuf<uint32_t> nt, nf, toff, foff;
+    SS_TRY(nt.alloc((size_t)R + 1));
+    SS_TRY(nf.alloc((size_t)R + 1));
+    SS_TRY(toff.alloc((size_t)R + 1));
+    SS_TRY(foff.alloc((size_t)R + 1));
+    SS_CUDA(cudaMemsetAsync(nt.p, 0, ((size_t)R + 1) * 4, st));
+    SS_CUDA(cudaMemsetAsync(nf.p, 0, ((size_t)R + 1) * 4, st));
+    k_count_tasks<<<ss::div_up(R, 256), 256, 0, st>>>(s->in_ptr.p, R, nt.p, nf.p);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, nt.p, toff.p, (int)(R + 1), st);
+    ss::DevBuf<char> tmp;
+    SS_TRY(tmp.alloc(tmp_bytes));
+    SS_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, nt.p, toff.p, (int)(R + 1), st));
+    SS_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, nf.p, foff.p, (int)(R + 1), st));
+    uint32_t n_tasks = 0, n_fix = 0;
+    SS_CUDA(cudaMemcpyAsync(&n_tasks, toff.p + R, 4, cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaMemcpyAsync(&n_fix, foff.p + R, 4, cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaStreamSynchronize(st));
+    s->n_tasks = n_tasks;
+    s->n_fix = n_fix;
+    if (n_tasks) {
+      ss::DevBuf<LongTask> unsorted;
+      ss::DevBuf<uint32_t> keys, keys_out, order, order_out;
+      SS_TRY(unsorted.alloc(n_tasks));
+      SS_TRY(s->tasks.alloc(n_tasks));
+      SS_TRY(s->fix.alloc(n_fix));
+      SS_TRY(keys.alloc(n_tasks));
+      SS_TRY(keys_out.alloc(n_tasks));
+      SS_TRY(order.alloc(n_tasks));
+      SS_TRY(order_out.alloc(n_tasks));
+      k_fill_tasks<<<ss::div_up(R, 256), 256, 0, st>>>(s->in_ptr.p, s->in_src.p, R, nt.p, toff.p, foff.p,
+                                                       unsorted.p, keys.p, order.p, s->fix.p);
+      size_t sort_bytes = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys.p, keys_out.p, order.p, order_out.p, (int)n_tasks,
+                                      0, 32, st);
+      ss::DevBuf<char> sort_tmp;
+      SS_TRY(sort_tmp.alloc(sort_bytes));
+      SS_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp.p, sort_bytes, keys.p, keys_out.p, order.p, order_out.p,
+                                              (int)n_tasks, 0, 32, st));
+      k_gather_tasks<<<ss::div_up(n_tasks, 256), 256, 0, st>>>(unsorted.p, order_out.p, n_tasks, s->tasks.p);
+      SS_CUDA(cudaStreamSynchronize(st));
+    }
+  }
+  SS_CUDA(cudaGetLastError());
+  for (auto& ev : s->ev) SS_CUDA(cudaEventCreate(&ev));
+  s->stats.n_nodes = N;
+  s->stats.n_edges = E;
+  s->stats.local_rows = s->rows_loc;
+  s->stats.local_edges = s->E_loc;
+  s->stats.load_ms =
+      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  e->pr = s;
+  s = nullptr;  // ownership moved
+  return SS_OK;
+}
+
+SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topics, const int64_t* num_pages,
+                       uint32_t max_iters, double* out_rank, uint32_t* out_iters) {
+  SS_REQUIRE(e, SS_ERR_INVALID, "ss_pagerank: engine is NULL");
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  PagerankState* s = e->pr;
+  SS_REQUIRE(s, SS_ERR_STATE, "ss_pagerank: no graph loaded");
+  SS_REQUIRE(n_topics == 0 || num_pages, SS_ERR_INVALID, "ss_pagerank: num_pages is NULL");
+  SS_REQUIRE(n_topics <= 16, SS_ERR_INVALID,
+             "ss_pagerank: %u topics; run topics in slabs of <= 16 (they are independent)", n_topics);
+  s->have_result = false;
+  s->stats.sweeps = 0;
+  s->stats.launches = 0;
+  s->stats.sweep_ms_total = s->stats.gather_ms_total = s->stats.exchange_ms_total = 0;
+  if (n_topics == 0) {  // empty forw[5]: every node gets {} (pagerank.go:53-63)
+    s->T = 0;
+    s->have_result = true;
+    return SS_OK;
+  }
+  cudaStream_t st = e->stream;
+  const int world = comm_world(e);
+  const int LPR = lpr_for_topics(n_topics), TP = 2 * LPR, T = (int)n_topics;
+  const uint64_t N = s->N;
+  const uint32_t R = s->rows_loc;
+  const bool timing = (e->flags & SS_FLAG_TIMING) != 0;
+  s->TP = TP;
+  s->T = T;
+  s->damping = damping;
+
+  const int GPC = (32 / LPR) * (kThreads / 32);
+  const uint32_t n_row_blocks = ss::div_up(R, GPC);
+  const uint32_t grid_short = std::max(1u, std::min<uint32_t>(n_row_blocks, (uint32_t)e->sm_count * 8));
+  const uint32_t grid_long =
+      std::max(1u, std::min<uint32_t>(ss::div_up(s->n_tasks, kThreads / 32), (uint32_t)e->sm_count * 8));
+  const uint32_t grid_fix = std::max(1u, std::min<uint32_t>(s->n_fix, (uint32_t)e->sm_count * 8));
+  const uint32_t grid_init = (uint32_t)e->sm_count * 8;
+  const uint32_t red_slots = std::max(grid_short + grid_long + grid_fix, grid_init);
+  const int W = 3 * TP;
+
+  if (s->y[0].n != N * TP) {
+    SS_TRY(s->y[0].alloc(N * TP));
+    SS_TRY(s->y[1].alloc(N * TP));
+  }
+  if (s->mul.n != std::max<size_t>(R, 1)) SS_TRY(s->mul.alloc(R));
+  if (s->partials.n != std::max<size_t>((size_t)s->n_tasks * TP, 1)) SS_TRY(s->partials.alloc((size_t)s->n_tasks * TP));
+  if (s->red.n != (size_t)red_slots * W) SS_TRY(s->red.alloc((size_t)red_slots * W));
+  if (s->sums.n != (size_t)W) SS_TRY(s->sums.alloc(W));
+  if (s->tot.n != (size_t)TP) SS_TRY(s->tot.alloc(TP));
+  if (s->init.n != (size_t)TP) SS_TRY(s->init.alloc(TP));
+
+  double h_init[16];
+  for (int t = 0; t < TP; ++t) h_init[t] = t < T ? 1.0 / (double)num_pages[t] : 0.0;  // pagerank.go:104
+  SS_CUDA(cudaMemcpyAsync(s->init.p, h_init, TP * 8, cudaMemcpyHostToDevice, st));
+
+  const double tele = 1.0 - damping;  // pagerank.go:90
+  std::vector<size_t> byte_off(world), byte_cnt(world);
+  for (int r = 0; r < world; ++r) {
+    byte_off[r] = (size_t)s->bounds[r] * TP * 8;
+    byte_cnt[r] = (size_t)(s->bounds[r + 1] - s->bounds[r]) * TP * 8;
+  }
+
+  // y0, mul, S_0
+  int rc = dispatch_lpr(LPR, [&](auto lpr) {
+    constexpr int L = decltype(lpr)::value;
+    k_init<L><<<grid_init, kThreads, 0, st>>>(s->y[0].p, s->outdeg.p, N, damping, s->init.p, s->row_lo, R, s->mul.p,
+                                             s->red.p);
+    return SS_OK;
+  });
+  SS_TRY(rc);
+  k_reduce_partials<<<1, kReduceThreads, 0, st>>>(s->red.p, grid_init, W, s->sums.p);
+  SS_TRY(comm_allreduce_sum_f64(e, s->sums.p, W));
+  k_finish_tot<<<1, 32, 0, st>>>(s->sums.p, TP, tele, (double)N, s->tot.p);
+  s->stats.launches += 3;
+  s->cur = 0;
+
+  uint32_t active = T >= 32 ? 0xFFFFFFFFu : ((1u << T) - 1u);
+  std::vector<uint32_t> iters(T, 0);
+  std::vector<double> h_sums(W);
+  bool hit_max = false;
+  for (uint32_t sweep = 1; active; ++sweep) {
+    SweepParams p;
+    p.y_last = s->y[s->cur].p;
+    p.y_next = s->y[s->cur ^ 1].p;
+    p.in_ptr = s->in_ptr.p;
+    p.in_src = s->in_src.p;
+    p.mul = s->mul.p;
+    p.tot = s->tot.p;
+    p.init = s->init.p;
+    p.row_lo = s->row_lo;
+    p.rows_loc = R;
+    p.active_mask = active;
+    p.tele = tele;
+    p.first = sweep == 1;
+    if (timing) SS_CUDA(cudaEventRecord(s->ev[0], st));
+    rc = dispatch_lpr(LPR, [&](auto lpr) {
+      constexpr int L = decltype(lpr)::value;
+      SweepParams q = p;
+      q.red = s->red.p;
+      k_sweep_short<L><<<grid_short, kThreads, 0, st>>>(q, n_row_blocks);
+      q.red = s->red.p + (size_t)grid_short * W;
+      k_sweep_long<L><<<grid_long, kThreads, 0, st>>>(q, s->tasks.p, s->n_tasks, s->partials.p);
+      if (timing) cudaEventRecord(s->ev[1], st);
+      q.red = s->red.p + (size_t)(grid_short + grid_long) * W;
+      k_sweep_fix<L><<<grid_fix, kThreads, 0, st>>>(q, s->fix.p, s->n_fix, s->partials.p);
+      return SS_OK;
+    });
+    SS_TRY(rc);
+    k_reduce_partials<<<1, kReduceThreads, 0, st>>>(s->red.p, grid_short + grid_long + grid_fix, W, s->sums.p);
+    if (timing) SS_CUDA(cudaEventRecord(s->ev[2], st));
+    if (world > 1) {
+      SS_TRY(comm_allgatherv_bytes(e, p.y_next, byte_off.data(), byte_cnt.data()));
+      SS_TRY(comm_allreduce_sum_f64(e, s->sums.p, W));
+    }
+    k_finish_tot<<<1, 32, 0, st>>>(s->sums.p, TP, tele, (double)N, s->tot.p);
+    if (timing) SS_CUDA(cudaEventRecord(s->ev[3], st));
+    SS_CUDA(cudaMemcpyAsync(h_sums.data(), s->sums.p, W * 8, cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaStreamSynchronize(st));
+    SS_CUDA(cudaGetLastError());
+    s->stats.launches += 5;
+    s->stats.sweeps = sweep;
+    if (timing) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, s->ev[0], s->ev[2]);
+      s->stats.sweep_ms_total += ms;
+      cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]);
+      s->stats.gather_ms_total += ms;
+      cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]);
+      s->stats.exchange_ms_total += ms;
+    }
+    s->cur ^= 1;
+    for (int t = 0; t < T; ++t) {
+      if (!((active >> t) & 1u)) continue;
+      iters[t] = sweep;
+      const double delta = h_sums[t], changed = h_sums[2 * TP + t];
+      // `for ...; lastChange > convergenceCriterion; ...` (pagerank.go:93): NaN ends the loop too
+      bool go_on = delta > eps;
+      if (go_on && changed == 0.0) go_on = false;  // bit-for-bit fixed point
+      if (go_on && max_iters && sweep >= max_iters) {
+        go_on = false;
+        hit_max = true;
+      }
+      if (!go_on) active &= ~(1u << t);
+    }
+  }
+  s->have_result = true;
+  if (out_iters) memcpy(out_iters, iters.data(), T * sizeof(uint32_t));
+  if (out_rank && N) {
+    // the state is replicated on every rank after the exchange: unscale all rows
+    // in bounded chunks and copy them out
+    const uint64_t chunk_rows = std::max<uint64_t>(1, (64ull << 20) / ((uint64_t)T * 8));
+    ss::DevBuf<double> stage;
+    SS_TRY(stage.alloc(std::min<uint64_t>(chunk_rows, N) * T));
+    for (uint64_t lo = 0; lo < N; lo += chunk_rows) {
+      const uint64_t hi = std::min<uint64_t>(lo + chunk_rows, N);
+      const uint64_t total = (hi - lo) * T;
+      k_unscale<<<ss::div_up(total, 256), 256, 0, st>>>(s->y[s->cur].p, s->outdeg.p, damping, TP, T, lo, hi, stage.p);
+      SS_CUDA(cudaMemcpyAsync(out_rank + lo * T, stage.p, total * 8, cudaMemcpyDeviceToHost, st));
+      SS_CUDA(cudaStreamSynchronize(st));
+      s->stats.launches += 1;
+    }
+  }
+  return hit_max ? SS_NOT_CONVERGED : SS_OK;
+}
+
+SS_API int ss_pagerank_fetch(ss_engine* e, uint64_t row_lo, uint64_t row_hi, double* out_rank) {
+  SS_REQUIRE(e && out_rank, SS_ERR_INVALID, "ss_pagerank_fetch: NULL argument");
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  PagerankState* s = e->pr;
+  SS_REQUIRE(s && s->have_result, SS_ERR_STATE, "ss_pagerank_fetch: no result");
+  SS_REQUIRE(row_lo <= row_hi && row_hi <= s->N, SS_ERR_INVALID, "ss_pagerank_fetch: bad row range");
+  if (s->T == 0 || row_lo == row_hi) return SS_OK;
+  cudaStream_t st = e->stream;
+  const int T = s->T;
+  const uint64_t chunk_rows = std::max<uint64_t>(1, (64ull << 20) / ((uint64_t)T * 8));
+  ss::DevBuf<double> stage;
+  SS_TRY(stage.alloc(std::min<uint64_t>(chunk_rows, row_hi - row_lo) * T));
+  for (uint64_t lo = row_lo; lo < row_hi; lo += chunk_rows) {
+    const uint64_t hi = std::min<uint64_t>(lo + chunk_rows, row_hi);
+    const uint64_t total = (hi - lo) * T;
+    k_unscale<<<ss::div_up(total, 256), 256, 0, st>>>(s->y[s->cur].p, s->outdeg.p, s->damping, s->TP, T, lo, hi,
+                                                      stage.p);
+    SS_CUDA(cudaMemcpyAsync(out_rank + (lo - row_lo) * T, stage.p, total * 8, cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaStreamSynchronize(st));
+  }
+  return SS_OK;
+}
+
+SS_API int ss_pagerank_get_stats(ss_engine* e, ss_pagerank_stats* out) {
+  SS_REQUIRE(e && out, SS_ERR_INVALID, "ss_pagerank_get_stats: NULL argument");
+  std::lock_guard<std::mutex> lock(e->mu);
+  SS_REQUIRE(e->pr, SS_ERR_STATE, "ss_pagerank_get_stats: no graph loaded");
+  *out = e->pr->stats;
+  return SS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+"""The oracle against the known-answer fixtures (tests/golden/kats.json) and
+its own cross-checks.  CPU only."""
+import json
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import loader as O
+from spaghettisearch_b200 import synth
+
+KATS = json.loads((Path(__file__).parent / "golden" / "kats.json").read_text())
+
+
+def test_go_log2_exact_powers_of_two(built):
+    for e in range(-20, 40):
+        assert O.go_log2(2.0 ** e) == float(e)
+    # log.go special cases
+    assert math.isnan(O.go_log(-1.0))
+    assert O.go_log(0.0) == -math.inf
+    assert O.go_log(math.inf) == math.inf
+    assert O.go_log(1.0) == 0.0
+
+
+def test_go_log2_close_to_libm(built):
+    rng = np.random.default_rng(0)
+    for x in rng.uniform(1.0, 1e8, 2000):
+        a, b = O.go_log2(float(x)), math.log2(float(x))
+        assert abs(a - b) <= 4 * np.spacing(b)
+
+
+def test_kat_pr1(built):
+    k = KATS["KAT-PR-1"]
+    for case in k["cases"]:
+        rank, iters = O.pagerank(k["row_ptr"], k["col_idx"], k["damping"], case["eps"], [case["num_pages"]],
+                                 case["max_iters"])
+        assert iters[0] == case["iters"]
+        assert rank[:, 0].tolist() == case["rank"]  # bit exact: same order of operations
+    # SURVEY.md §8(c) seed values
+    rank, iters = O.pagerank(k["row_ptr"], k["col_idx"], 0.75, 1e-20, [4, 10])
+    assert iters.tolist() == [30, 30]
+    assert rank[:, 0].tolist() == [0.2693673224993629, 0.24741289482615944, 0.3782054541450765,
+                                   0.17621361167778027]
+    assert rank[:, 0].tolist() == rank[:, 1].tolist()
+    rank, iters = O.pagerank(k["row_ptr"], k["col_idx"], 0.75, 1e-9, [4, 10])
+    assert iters.tolist() == [17, 17]
+    assert rank[0].tolist() == [0.2693673224920345, 0.26936732249513917]
+
+
+def test_pagerank_zero_pages_is_nan_after_one_sweep(built):
+    k = KATS["KAT-PR-1"]
+    rank, iters = O.pagerank(k["row_ptr"], k["col_idx"], 0.75, 1e-9, [0])
+    assert iters[0] == 1 and np.isnan(rank).all()
+
+
+def test_pagerank_variants_agree(built):
+    g = synth.graph(3000, 40000, seed=7)
+    npg = synth.topics(5)
+    ref, it_ref = O.pagerank(g.row_ptr, g.col_idx, 0.75, 1e-9, npg)
+    fair, it_fair, _ = O.pagerank_fair(g.row_ptr, g.col_idx, 0.75, 1e-9, npg, n_threads=4)
+    assert it_ref.tolist() == it_fair.tolist()
+    assert np.abs(ref - fair).sum(axis=0).max() < 1e-13
+    faith, it_f, secs = O.pagerank_faithful(g.row_ptr, g.col_idx, 0.75, 1e-9, int(npg[2]))
+    assert it_f == it_ref[2] and secs > 0
+    assert np.abs(ref[:, 2] - faith).sum() < 1e-13
+
+
+def test_kat_sc1(built):
+    k = KATS["KAT-SC-1"]
+    tabs = {}
+    for name in ("title", "body"):
+        t = k[name]
+        w, mag = O.term_weights(t["term_ptr"], t["doc_ids"], t["norm_tf"], k["n_docs"], k["total_docs"])
+        assert w.tolist() == k["w_" + name]
+        assert mag.tolist() == k["mag_" + name]
+        tabs[name] = (O.Table(t["term_ptr"], t["doc_ids"], w), mag)
+    docs, final, pr, count = O.score_batch(tabs["title"][0], tabs["body"][0], k["n_docs"], tabs["title"][1],
+                                           tabs["body"][1], None, [0, len(k["query"])], k["query"], k=50)
+    assert count[0] == 3
+    assert docs[0, :3].tolist() == [r["doc"] for r in k["result"]]
+    assert final[0, :3].tolist() == [r["final"] for r in k["result"]]
+    assert (pr[0] == 0).all() and (docs[0, 3:] == 0xFFFFFFFF).all()
+    # SURVEY.md §8(c) seed values
+    assert final[0, :3].tolist() == [47.376154339498676, 27.5118156434649, 3.371181523570759]
+
+
+def _tiny_index():
+    # docs 0..5, terms 0..3; body with positions, title with positions incl. the -100 sentinel
+    body = {0: {0: (0.5, [1, 7]), 1: (1.0, [2]), 4: (0.25, [9])},
+            1: {0: (1.0, [2, 30]), 1: (0.5, [5]), 2: (1.0, [0])},
+            2: {0: (0.75, [3]), 3: (1.0, [4])},
+            3: {5: (1.0, [])}}
+    title = {0: {1: (1.0, [-100]), 2: (0.5, [0])},
+             1: {2: (1.0, [1]), 3: (1.0, [-100])},
+             2: {0: (1.0, [-100]), 1: (0.5, [-100])}}
+
+    def csc(tab, n_terms):
+        ptr, docs, tf, pp, pos = [0], [], [], [0], []
+        for t in range(n_terms):
+            for d in sorted(tab.get(t, {})):
+                docs.append(d)
+                tf.append(tab[t][d][0])
+                pos.extend(tab[t][d][1])
+                pp.append(len(pos))
+            ptr.append(len(docs))
+        return (np.array(ptr, np.uint64), np.array(docs, np.uint32), np.array(tf, np.float32),
+                np.array(pp, np.uint64), np.array(pos, np.float32))
+
+    return csc(title, 4), csc(body, 4), 6
+
+
+def _weighted(built, total_docs=6.0):
+    (tp, td, ttf, tpp, tpos), (bp, bd, btf, bpp, bpos), n_docs = _tiny_index()
+    tw, tmag = O.term_weights(tp, td, ttf, n_docs, total_docs)
+    bw, bmag = O.term_weights(bp, bd, btf, n_docs, total_docs)
+    return O.Table(tp, td, tw, tpp, tpos), O.Table(bp, bd, bw, bpp, bpos), tmag, bmag, n_docs
+
+
+def test_intersect_util(built):
+    assert O.intersect([3, 1, 2], [2, 3, 4]) == [2, 3]
+    assert O.intersect([1, 1, 2], [1, 1, 1]) == [1, 1]  # multiset: util.go advances both cursors
+    assert O.intersect(None, [1]) == [] and O.intersect([1], None) == []
+    assert O.intersect([], [1]) == []
+
+
+def test_phrase_semantics(built):
+    title, body, tmag, bmag, n_docs = _weighted(built)
+    qm2 = math.sqrt(2.0)
+
+    def run(kw, ph):
+        kw_ptr, ph_ptr = [0, len(kw)], [0, len(ph)]
+        d, f, p, c = O.score_batch(title, body, n_docs, tmag, bmag, None, kw_ptr, kw, ph_ptr, ph, k=10)
+        return d[0, :c[0]].tolist(), f[0, :c[0]].tolist()
+
+    # phrase [t0 t1]: body adjacency needs pos(t1) = pos(t0)+1.  doc0: t0@{1,7}, t1@{2,30} -> match;
+    # doc1: t0@{2}, t1@{5} -> no.  Title: doc2 has t0@0 and t1@1 -> title match.
+    docs, final = run([], [0, 1])
+    assert sorted(docs) == [0, 2]
+    w_b = float(np.float32(body.w[0] + body.w[3]))  # fp32 sum in phrase order, phrase.go:59,83
+    exp0 = (0.38 * 0.0 + 0.29 * (w_b / (bmag[0] * qm2))) * 100.0
+    assert final[docs.index(0)] == exp0
+    # the -100 sentinel aligns for a ONE word phrase (phrase.go:68-75), never across words
+    docs, _ = run([], [2])
+    assert sorted(docs) == [0, 1, 3]
+    # doc1 has t0@-100 and t2@-100 in its title: both slots filled, but -100 and -100-1 never align,
+    # and t2 has no body posting in doc1 -> not a match.  doc0 matches in the body (t0@3? no: t0@{1,7},
+    # t2@{3} -> 3-1=2 not in {1,7}) -> nothing at all.
+    docs, _ = run([], [0, 2])
+    assert docs == []
+    docs, _ = run([], [1, 2])  # body doc0: t1@{2,30}, t2@{3} -> 3-1 = 2 aligns
+    assert docs == [0]
+    # a posting without positions cannot match even a one-word phrase
+    docs, _ = run([], [3])
+    assert docs == []
+    # keyword + phrase: queryLength counts both (main_retrieve.go:90)
+    docs, final = run([3], [0, 1])
+    assert 5 in docs and 0 in docs
+    # unknown term ids are empty rows; a phrase with an unknown term matches nothing
+    docs, _ = run([99], [0, 99])
+    assert docs == []
+
+
+def test_duplicate_query_terms_count_twice(built):
+    title, body, tmag, bmag, n_docs = _weighted(built)
+    d1, f1, _, c1 = O.score_batch(title, body, n_docs, tmag, bmag, None, [0, 1], [0], k=10)
+    d2, f2, _, c2 = O.score_batch(title, body, n_docs, tmag, bmag, None, [0, 2], [0, 0], k=10)
+    assert c1[0] == c2[0]
+    # sums double, |q| goes 1 -> sqrt(2): scores scale by sqrt(2)
+    m1 = dict(zip(d1[0, :c1[0]].tolist(), f1[0, :c1[0]].tolist()))
+    m2 = dict(zip(d2[0, :c2[0]].tolist(), f2[0, :c2[0]].tolist()))
+    for d in m1:
+        assert m2[d] == pytest.approx(m1[d] * math.sqrt(2.0), rel=1e-15)
+
+
+def test_idf_zero_gives_zero_not_nan(built):
+    # df == totalDocs -> idf = 0 -> w = 0, mag = 0 -> 0/0 = NaN -> 0 (get_metadata.go:61-66)
+    ptr = np.array([0, 3], np.uint64)
+    docs = np.array([0, 1, 2], np.uint32)
+    tf = np.array([1.0, 0.5, 0.25], np.float32)
+    w, mag = O.term_weights(ptr, docs, tf, 3, 3.0)
+    assert (w == 0).all() and (mag == 0).all()
+    tab = O.Table(ptr, docs, w)
+    empty = O.Table(np.array([0, 0], np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.float32))
+    d, f, p, c = O.score_batch(empty, tab, 3, mag, mag, None, [0, 1], [0], k=5)
+    assert c[0] == 3 and d[0, :3].tolist() == [0, 1, 2] and (f[0, :3] == 0).all()
+
+
+def test_blend_and_tie_order(built):
+    title, body, tmag, bmag, n_docs = _weighted(built)
+    rng = np.random.default_rng(3)
+    pr = rng.uniform(0, 1e-3, (n_docs, 4))
+    probs = np.array([0.1, 0.2, 0.3, 0.4])
+    d, f, p, c = O.score_batch(title, body, n_docs, tmag, bmag, pr, [0, 2], [0, 1], topic_probs=probs, k=10)
+    for j in range(c[0]):
+        sqd = 0.0
+        for t in range(4):
+            sqd += probs[t] * pr[d[0, j], t]
+        assert p[0, j] == sqd
+    assert all(f[0, j] >= f[0, j + 1] for j in range(c[0] - 1))
+    # per-query probabilities
+    probs2 = np.stack([probs, probs[::-1]])
+    d2, f2, p2, c2 = O.score_batch(title, body, n_docs, tmag, bmag, pr, [0, 2, 4], [0, 1, 0, 1],
+                                   topic_probs=probs2, k=10)
+    assert d2[0].tolist() == d[0].tolist() and f2[0].tolist() == f[0].tolist()
+    assert not np.array_equal(p2[0], p2[1])
