@@ -118,6 +118,9 @@ SS_API int ss_index_load(ss_engine* e, int table, uint64_t n_terms, uint64_t n_d
                          const uint64_t* term_ptr, const uint32_t* doc_ids,
                          const float* norm_tf, const uint64_t* pos_ptr, const float* pos);
 
+/* Drop both tables, their norms and the blend input (before loading another index). */
+SS_API int ss_index_clear(ss_engine* e);
+
 /* idf = float32(log2(total_docs / df)) with Go's Log2, w = norm_tf * idf in
  * fp32, mag[doc] = sqrt(sum float64(float32(w*w))), ascending term order.
  * df_global: NULL => df = this table's row length; else [n_terms] (doc-sharded

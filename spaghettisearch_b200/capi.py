@@ -21,6 +21,7 @@ SS_FLAG_TIMING = 1
 EXPORTS = [
     "ss_version", "ss_create", "ss_destroy", "ss_last_error", "ss_comm_unique_id", "ss_comm_init",
     "ss_graph_load_csr", "ss_pagerank", "ss_pagerank_fetch", "ss_pagerank_get_stats", "ss_index_load",
+    "ss_index_clear",
     "ss_term_weights", "ss_set_doc_norms", "ss_set_pagerank", "ss_use_pagerank", "ss_score_batch",
     "ss_merge_topk", "ss_score_get_stats",
 ]
@@ -80,6 +81,7 @@ def load():
     L.ss_pagerank_fetch.argtypes = [vp, u64, u64, vp]
     L.ss_pagerank_get_stats.argtypes = [vp, C.POINTER(PagerankStats)]
     L.ss_index_load.argtypes = [vp, C.c_int, u64, u64, vp, vp, vp, vp, vp]
+    L.ss_index_clear.argtypes = [vp]
     L.ss_term_weights.argtypes = [vp, C.c_int, dbl, vp, vp, vp]
     L.ss_set_doc_norms.argtypes = [vp, C.c_int, u64, vp]
     L.ss_set_pagerank.argtypes = [vp, u64, u32, vp]
@@ -194,6 +196,9 @@ class Engine:
         pos_ptr, pos = _as(pos_ptr, np.uint64), _as(pos, np.float32)
         self._check(self.L.ss_index_load(self.h, table, len(term_ptr) - 1, n_docs, _ptr(term_ptr),
                                          _ptr(doc_ids), _ptr(norm_tf), _ptr(pos_ptr), _ptr(pos)))
+
+    def index_clear(self):
+        self._check(self.L.ss_index_clear(self.h))
 
     def term_weights(self, table, total_docs, n_postings, n_docs, df_global=None, want=True):
         df_global = _as(df_global, np.uint64)

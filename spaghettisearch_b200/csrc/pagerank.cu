@@ -84,26 +84,28 @@ struct Acc {  // per-thread running sums for its two topic columns
 };
 
 // Fused normalise / teleport / residual for one finished row; executed by the
-// LPR lanes that own the row, lane l8 holding topics 2*l8 and 2*l8+1.
+// LPR lanes that own the row, lane l8 holding topics 2*l8 and 2*l8+1.  The
+// row's own previous value yl and scale m are loaded by the caller (early, so
+// that they overlap the gathers).
 template <int LPR>
 __device__ __forceinline__ void epilogue(const SweepParams& p, uint32_t r, int l8, double a0, double a1,
-                                         Acc& acc) {
+                                         double2 yl, double m, Acc& acc) {
   constexpr int TP = 2 * LPR;
   const uint64_t v = p.row_lo + r;
-  const double m = p.mul[r];
   const bool has_out = m > 0.0;
   const double mul = has_out ? m : 1.0;
-  const double2 yl = ld_row_stream(p.y_last + v * TP + 2 * l8);
+  const double2 tot = *reinterpret_cast<const double2*>(p.tot + 2 * l8);
   double2 yn;
   {
     const int t = 2 * l8;
     double last_rank = yl.x / mul;
     if (p.first) {
-      a0 += p.init[t];
-      last_rank = p.init[t];
+      const double i0 = p.init[t];
+      a0 += i0;
+      last_rank = i0;
     }
     if ((p.active_mask >> t) & 1u) {
-      double nr = (a0 + p.tele) / p.tot[t];
+      double nr = (a0 + p.tele) / tot.x;
       acc.d0 += fabs(nr - last_rank);
       yn.x = nr * mul;
       acc.c0 += (__double_as_longlong(yn.x) != __double_as_longlong(yl.x)) ? 1.0 : 0.0;
@@ -116,11 +118,12 @@ __device__ __forceinline__ void epilogue(const SweepParams& p, uint32_t r, int l
     const int t = 2 * l8 + 1;
     double last_rank = yl.y / mul;
     if (p.first) {
-      a1 += p.init[t];
-      last_rank = p.init[t];
+      const double i1 = p.init[t];
+      a1 += i1;
+      last_rank = i1;
     }
     if ((p.active_mask >> t) & 1u) {
-      double nr = (a1 + p.tele) / p.tot[t];
+      double nr = (a1 + p.tele) / tot.y;
       acc.d1 += fabs(nr - last_rank);
       yn.y = nr * mul;
       acc.c1 += (__double_as_longlong(yn.y) != __double_as_longlong(yl.y)) ? 1.0 : 0.0;
@@ -165,43 +168,79 @@ __device__ __forceinline__ void block_reduce(const SweepParams& p, Acc acc, bool
   }
 }
 
+// One gather step of an LPR-lane group: LPR source ids come from the group's
+// `idx` registers (lane j of the group holds edge j); all LPR row loads are
+// issued before any add so that they are in flight together.  Invalid slots
+// (kNone) load row 0 and add nothing.
+template <int LPR, int STRIDE>
+__device__ __forceinline__ void gather_step(const double* __restrict__ y, unsigned mask, uint32_t idx, int first_lane,
+                                            int l8, double& a0, double& a1) {
+  constexpr int TP = 2 * LPR;
+  double2 rows[LPR];
+  bool ok[LPR];
+#pragma unroll
+  for (int j = 0; j < LPR; ++j) {
+    const uint32_t u = __shfl_sync(mask, idx, first_lane + j * STRIDE);
+    ok[j] = u != kNone;
+    rows[j] = ld_row_gather(y + (uint64_t)(ok[j] ? u : 0u) * TP + 2 * l8);
+  }
+#pragma unroll
+  for (int j = 0; j < LPR; ++j) {
+    a0 += ok[j] ? rows[j].x : 0.0;
+    a1 += ok[j] ? rows[j].y : 0.0;
+  }
+}
+
 // Rows with in-degree <= kShortMax: one row per LPR-lane group, 32/LPR rows
-// per warp, consecutive rows in consecutive groups (coalesced y rows).
+// per warp, consecutive rows in consecutive groups (coalesced y rows).  The
+// row pointers of the next row block and this row's own y/scale are fetched
+// before the gathers so that only index -> row remains a dependent chain.
 template <int LPR>
-__global__ void __launch_bounds__(kThreads) k_sweep_short(SweepParams p, uint32_t n_row_blocks) {
+__global__ void __launch_bounds__(kThreads, 4) k_sweep_short(SweepParams p, uint32_t n_row_blocks) {
   constexpr int TP = 2 * LPR, GPW = 32 / LPR, GPC = GPW * (kThreads / 32);
   const int lane = threadIdx.x & 31, l8 = lane % LPR, g = lane / LPR;
   const unsigned gmask = (LPR == 32 ? 0xFFFFFFFFu : ((1u << LPR) - 1u)) << (g * LPR);
   const int group_in_cta = (threadIdx.x >> 5) * GPW + g;
   Acc acc;
-  for (uint32_t rb = blockIdx.x; rb < n_row_blocks; rb += gridDim.x) {
+  uint32_t rb = blockIdx.x;
+  uint64_t b_n = 0, e_n = 0;
+  {
     const uint32_t r = rb * GPC + group_in_cta;
+    if (rb < n_row_blocks && r < p.rows_loc) {
+      b_n = p.in_ptr[r];
+      e_n = p.in_ptr[r + 1];
+    }
+  }
+  for (; rb < n_row_blocks; rb += gridDim.x) {
+    const uint32_t r = rb * GPC + group_in_cta;
+    const uint64_t b = b_n, e = e_n;
+    {
+      const uint32_t rbn = rb + gridDim.x, rn = rbn * GPC + group_in_cta;
+      if (rbn < n_row_blocks && rn < p.rows_loc) {
+        b_n = p.in_ptr[rn];
+        e_n = p.in_ptr[rn + 1];
+      }
+    }
     if (r >= p.rows_loc) continue;
-    const uint64_t b = p.in_ptr[r], e = p.in_ptr[r + 1];
     if (e - b > kShortMax) continue;  // a long row: k_sweep_long / k_sweep_fix own it
+    const double2 yl = ld_row_stream(p.y_last + (p.row_lo + r) * TP + 2 * l8);
+    const double m = p.mul[r];
     double a0 = 0, a1 = 0;
     for (uint64_t i = b; i < e; i += LPR) {
       const uint32_t idx = (i + l8 < e) ? __ldg(p.in_src + i + l8) : kNone;
-#pragma unroll
-      for (int j = 0; j < LPR; ++j) {
-        const uint32_t u = __shfl_sync(gmask, idx, g * LPR + j);
-        if (u != kNone) {
-          const double2 row = ld_row_gather(p.y_last + (uint64_t)u * TP + 2 * l8);
-          a0 += row.x;
-          a1 += row.y;
-        }
-      }
+      gather_step<LPR, 1>(p.y_last, gmask, idx, g * LPR, l8, a0, a1);
     }
-    epilogue<LPR>(p, r, l8, a0, a1, acc);
+    epilogue<LPR>(p, r, l8, a0, a1, yl, m, acc);
   }
   block_reduce<LPR>(p, acc, true);
 }
 
 // Long-row tasks: one warp per task, 32 edges per step, group g takes edges
-// j*GPW+g; the GPW partial rows are combined with shuffles.
+// j*GPW+g; the GPW partial rows are combined with shuffles.  The next step's
+// indices are fetched before this step's rows.
 template <int LPR>
-__global__ void __launch_bounds__(kThreads) k_sweep_long(SweepParams p, const LongTask* __restrict__ tasks,
-                                                        uint32_t n_tasks, double* __restrict__ partials) {
+__global__ void __launch_bounds__(kThreads, 4) k_sweep_long(SweepParams p, const LongTask* __restrict__ tasks,
+                                                           uint32_t n_tasks, double* __restrict__ partials) {
   constexpr int TP = 2 * LPR, GPW = 32 / LPR;
   const int lane = threadIdx.x & 31, l8 = lane % LPR, g = lane / LPR;
   const uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5;
@@ -210,18 +249,18 @@ __global__ void __launch_bounds__(kThreads) k_sweep_long(SweepParams p, const Lo
   for (uint32_t ti = warp; ti < n_tasks; ti += n_warps) {
     const LongTask t = tasks[ti];
     const uint32_t* src = p.in_src + t.e_begin;
+    double2 yl = make_double2(0, 0);
+    double m = 0;
+    if (t.slot < 0 && g == 0) {
+      yl = ld_row_stream(p.y_last + (p.row_lo + t.row) * TP + 2 * l8);
+      m = p.mul[t.row];
+    }
     double a0 = 0, a1 = 0;
+    uint32_t idx_next = lane < t.n ? __ldg(src + lane) : kNone;
     for (uint32_t i = 0; i < t.n; i += 32) {
-      const uint32_t idx = (i + lane < t.n) ? __ldg(src + i + lane) : kNone;
-#pragma unroll
-      for (int j = 0; j < LPR; ++j) {
-        const uint32_t u = __shfl_sync(0xFFFFFFFFu, idx, j * GPW + g);
-        if (u != kNone) {
-          const double2 row = ld_row_gather(p.y_last + (uint64_t)u * TP + 2 * l8);
-          a0 += row.x;
-          a1 += row.y;
-        }
-      }
+      const uint32_t idx = idx_next;
+      idx_next = (i + 32 + lane < t.n) ? __ldg(src + i + 32 + lane) : kNone;
+      gather_step<LPR, GPW>(p.y_last, 0xFFFFFFFFu, idx, g, l8, a0, a1);
     }
 #pragma unroll
     for (int o = LPR; o < 32; o <<= 1) {
@@ -230,7 +269,7 @@ __global__ void __launch_bounds__(kThreads) k_sweep_long(SweepParams p, const Lo
     }
     if (g == 0) {
       if (t.slot < 0) {
-        epilogue<LPR>(p, t.row, l8, a0, a1, acc);
+        epilogue<LPR>(p, t.row, l8, a0, a1, yl, m, acc);
       } else {
         *reinterpret_cast<double2*>(partials + (size_t)t.slot * TP + 2 * l8) = make_double2(a0, a1);
       }
@@ -251,6 +290,12 @@ __global__ void __launch_bounds__(kThreads) k_sweep_fix(SweepParams p, const Fix
   Acc acc;
   for (uint32_t fi = blockIdx.x; fi < n_fix; fi += gridDim.x) {
     const FixRow fr = rows[fi];
+    double2 yl = make_double2(0, 0);
+    double m = 0;
+    if (warp == 0 && g == 0) {
+      yl = ld_row_stream(p.y_last + (p.row_lo + fr.row) * TP + 2 * l8);
+      m = p.mul[fr.row];
+    }
     double a0 = 0, a1 = 0;
     for (uint32_t s = group_in_cta; s < fr.n_slots; s += GPC) {
       const double2 v = *reinterpret_cast<const double2*>(partials + (size_t)(fr.first_slot + s) * TP + 2 * l8);
@@ -272,34 +317,52 @@ __global__ void __launch_bounds__(kThreads) k_sweep_fix(SweepParams p, const Fix
         b0 += sm[w][l8].x;
         b1 += sm[w][l8].y;
       }
-      epilogue<LPR>(p, fr.row, l8, b0, b1, acc);
+      epilogue<LPR>(p, fr.row, l8, b0, b1, yl, m, acc);
     }
   }
   block_reduce<LPR>(p, acc, warp == 0 && g == 0);
 }
 
-// sums[0..width) = sum over all per-CTA partials, fixed stripe order (one CTA).
-constexpr int kReduceThreads = 1024;
-__global__ void __launch_bounds__(kReduceThreads) k_reduce_partials(const double* __restrict__ red, uint32_t n_slots,
-                                                                    int width, double* __restrict__ sums) {
-  __shared__ double sm[kReduceThreads];
-  const int stripes = kReduceThreads / width;
+// Two-stage fixed-order sum of the per-CTA partial rows: kReduceCtas CTAs each
+// fold a strided subset of the slots, then k_finish_tot folds those.
+constexpr int kReduceCtas = 32;
+__global__ void __launch_bounds__(kThreads) k_reduce_partials(const double* __restrict__ red, uint32_t n_slots,
+                                                              int width, double* __restrict__ stage) {
+  __shared__ double sm[kThreads];
+  const int stripes = kThreads / width;
   const int c = threadIdx.x % width, s = threadIdx.x / width;
   double v = 0;
   if (s < stripes) {
-#pragma unroll 8
-    for (uint32_t i = s; i < n_slots; i += stripes) v += red[(size_t)i * width + c];
+    const uint32_t step = gridDim.x * stripes;
+    uint32_t i = blockIdx.x * stripes + s;
+    for (; i + 3 * step < n_slots; i += 4 * step) {
+      const double x0 = red[(size_t)i * width + c], x1 = red[(size_t)(i + step) * width + c];
+      const double x2 = red[(size_t)(i + 2 * step) * width + c], x3 = red[(size_t)(i + 3 * step) * width + c];
+      v += x0;
+      v += x1;
+      v += x2;
+      v += x3;
+    }
+    for (; i < n_slots; i += step) v += red[(size_t)i * width + c];
   }
   sm[threadIdx.x] = (s < stripes) ? v : 0.0;
   __syncthreads();
   if (threadIdx.x < width) {
     double t = 0;
     for (int k = 0; k < stripes; ++k) t += sm[k * width + threadIdx.x];
-    sums[threadIdx.x] = t;
+    stage[(size_t)blockIdx.x * width + threadIdx.x] = t;
   }
 }
 
-// tot[t] = S_t + (1-d) N  (pagerank.go:111-112), after the cross-rank sum.
+// sums = fold of the staged rows; tot[t] = S_t + (1-d) N (pagerank.go:111-112).
+// With several ranks the fold and tot are split around the cross-rank sum.
+__global__ void k_fold_stage(const double* __restrict__ stage, int n_rows, int width, double* __restrict__ sums) {
+  const int c = threadIdx.x;
+  if (c >= width) return;
+  double t = 0;
+  for (int k = 0; k < n_rows; ++k) t += stage[(size_t)k * width + c];
+  sums[c] = t;
+}
 __global__ void k_finish_tot(const double* __restrict__ sums, int TP, double tele, double n_nodes,
                              double* __restrict__ tot) {
   const int t = threadIdx.x;
@@ -480,7 +543,7 @@ struct PagerankState {
   double damping = 0;
   ss::DevBuf<double> y[2];
   int cur = 0;  // y[cur] holds the latest ranks
-  ss::DevBuf<double> mul, partials, red, sums, tot, init;
+  ss::DevBuf<double> mul, partials, red, stage, sums, tot, init;
   bool have_result = false;
   ss_pagerank_stats stats{};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -700,9 +763,18 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
 
   const int GPC = (32 / LPR) * (kThreads / 32);
   const uint32_t n_row_blocks = ss::div_up(R, GPC);
-  const uint32_t grid_short = std::max(1u, std::min<uint32_t>(n_row_blocks, (uint32_t)e->sm_count * 8));
-  const uint32_t grid_long =
-      std::max(1u, std::min<uint32_t>(ss::div_up(s->n_tasks, kThreads / 32), (uint32_t)e->sm_count * 8));
+  int occ_short = 4, occ_long = 4;
+  dispatch_lpr(LPR, [&](auto lpr) {
+    constexpr int L = decltype(lpr)::value;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_short, k_sweep_short<L>, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_long, k_sweep_long<L>, kThreads, 0);
+    return SS_OK;
+  });
+  // persistent grids: exactly one resident wave, static block-cyclic work split
+  const uint32_t grid_short =
+      std::max(1u, std::min<uint32_t>(n_row_blocks, (uint32_t)(e->sm_count * std::max(1, occ_short))));
+  const uint32_t grid_long = std::max(
+      1u, std::min<uint32_t>(ss::div_up(s->n_tasks, kThreads / 32), (uint32_t)(e->sm_count * std::max(1, occ_long))));
   const uint32_t grid_fix = std::max(1u, std::min<uint32_t>(s->n_fix, (uint32_t)e->sm_count * 8));
   const uint32_t grid_init = (uint32_t)e->sm_count * 8;
   const uint32_t red_slots = std::max(grid_short + grid_long + grid_fix, grid_init);
@@ -716,6 +788,7 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
   if (s->partials.n != std::max<size_t>((size_t)s->n_tasks * TP, 1)) SS_TRY(s->partials.alloc((size_t)s->n_tasks * TP));
   if (s->red.n != (size_t)red_slots * W) SS_TRY(s->red.alloc((size_t)red_slots * W));
   if (s->sums.n != (size_t)W) SS_TRY(s->sums.alloc(W));
+  if (s->stage.n != (size_t)kReduceCtas * W) SS_TRY(s->stage.alloc((size_t)kReduceCtas * W));
   if (s->tot.n != (size_t)TP) SS_TRY(s->tot.alloc(TP));
   if (s->init.n != (size_t)TP) SS_TRY(s->init.alloc(TP));
 
@@ -738,10 +811,11 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
     return SS_OK;
   });
   SS_TRY(rc);
-  k_reduce_partials<<<1, kReduceThreads, 0, st>>>(s->red.p, grid_init, W, s->sums.p);
+  k_reduce_partials<<<kReduceCtas, kThreads, 0, st>>>(s->red.p, grid_init, W, s->stage.p);
+  k_fold_stage<<<1, 64, 0, st>>>(s->stage.p, kReduceCtas, W, s->sums.p);
   SS_TRY(comm_allreduce_sum_f64(e, s->sums.p, W));
   k_finish_tot<<<1, 32, 0, st>>>(s->sums.p, TP, tele, (double)N, s->tot.p);
-  s->stats.launches += 3;
+  s->stats.launches += 4;
   s->cur = 0;
 
   uint32_t active = T >= 32 ? 0xFFFFFFFFu : ((1u << T) - 1u);
@@ -776,7 +850,8 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
       return SS_OK;
     });
     SS_TRY(rc);
-    k_reduce_partials<<<1, kReduceThreads, 0, st>>>(s->red.p, grid_short + grid_long + grid_fix, W, s->sums.p);
+    k_reduce_partials<<<kReduceCtas, kThreads, 0, st>>>(s->red.p, grid_short + grid_long + grid_fix, W, s->stage.p);
+    k_fold_stage<<<1, 64, 0, st>>>(s->stage.p, kReduceCtas, W, s->sums.p);
     if (timing) SS_CUDA(cudaEventRecord(s->ev[2], st));
     if (world > 1) {
       SS_TRY(comm_allgatherv_bytes(e, p.y_next, byte_off.data(), byte_cnt.data()));
@@ -787,7 +862,7 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
     SS_CUDA(cudaMemcpyAsync(h_sums.data(), s->sums.p, W * 8, cudaMemcpyDeviceToHost, st));
     SS_CUDA(cudaStreamSynchronize(st));
     SS_CUDA(cudaGetLastError());
-    s->stats.launches += 5;
+    s->stats.launches += 6;
     s->stats.sweeps = sweep;
     if (timing) {
       float ms = 0;
@@ -856,6 +931,29 @@ SS_API int ss_pagerank_fetch(ss_engine* e, uint64_t row_lo, uint64_t row_hi, dou
   }
   return SS_OK;
 }
+
+}  // extern "C"
+
+// Unscaled copy of the last result, [N][T], for the scoring blend (index.cu).
+int pagerank_export_device(ss_engine* e, ss::DevBuf<double>* out, uint64_t* n_rows, uint32_t* n_topics) {
+  PagerankState* s = e->pr;
+  SS_REQUIRE(s && s->have_result, SS_ERR_STATE, "ss_use_pagerank: no PageRank result on the device");
+  *n_rows = s->N;
+  *n_topics = (uint32_t)s->T;
+  if (s->T == 0 || s->N == 0) {
+    out->reset();
+    return SS_OK;
+  }
+  SS_TRY(out->alloc(s->N * (uint64_t)s->T));
+  const uint64_t total = s->N * (uint64_t)s->T;
+  k_unscale<<<ss::div_up(total, 256), 256, 0, e->stream>>>(s->y[s->cur].p, s->outdeg.p, s->damping, s->TP, s->T, 0,
+                                                           s->N, out->p);
+  SS_CUDA(cudaStreamSynchronize(e->stream));
+  SS_CUDA(cudaGetLastError());
+  return SS_OK;
+}
+
+extern "C" {
 
 SS_API int ss_pagerank_get_stats(ss_engine* e, ss_pagerank_stats* out) {
   SS_REQUIRE(e && out, SS_ERR_INVALID, "ss_pagerank_get_stats: NULL argument");

@@ -1,0 +1,686 @@
+// HP-2 online: the score / blend / top-k core of retrieval.Retrieve
+// (retrieval/main_retrieve.go:15-104, get_metadata.go:16-77, phrase.go:11-170,
+// util.go:48-54,179-203) for a whole query batch.
+//
+// One CTA scores one (query, doc slab) pair.  The slab is walked in sub-ranges
+// of kRange docs whose two fp64 accumulators (TitleRank, BodyRank) live in
+// shared memory.  Per sub-range:
+//   1. every posting list of the query is narrowed to the sub-range by a
+//      galloping search from where the previous sub-range ended;
+//   2. keyword tokens are applied in query order, body and title lists
+//      together, a barrier between tokens: a list holds a doc at most once, so
+//      no atomics are needed and each doc's sum has the reference's token order
+//      (main_retrieve.go:61-69, 170-187);
+//   3. the phrase (main_retrieve.go:73-78, phrase.go) is applied last: the
+//      shortest list drives, the others are probed by binary search, positions
+//      are intersected with the reference's shifted-equality rule;
+//   4. matched docs are finished -- cosine, NaN -> 0, PageRank blend
+//      (get_metadata.go:53-69) -- and the few that beat the CTA's running k-th
+//      best go through a rank-by-counting merge into the running top-k.
+// CTAs are ordered slab-major so that concurrently running CTAs read the same
+// slice of the index and of the per-doc norms (L2 reuse across queries).
+// A final kernel merges the per-slab lists; the same kernel merges per-shard
+// lists for the doc-sharded multi-GPU path.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "index.cuh"
+
+namespace {
+
+constexpr int kT = 256;        // threads per CTA
+constexpr int kRange = 2048;   // docs per sub-range
+constexpr int kCand = 1024;    // doc slots finished per candidate round
+constexpr int kMaxK = 128;
+constexpr int kMaxKw = 64;     // keyword tokens per query handled in-kernel
+constexpr int kMaxPh = 32;     // phrase tokens per query handled in-kernel
+constexpr int kMaxLists = 2 * (kMaxKw + kMaxPh);
+constexpr uint32_t kNoDoc = 0xFFFFFFFFu;
+
+struct TableView {
+  const uint64_t* term_ptr;
+  const uint32_t* doc_ids;
+  const float* w;
+  const uint64_t* pos_ptr;
+  const float* pos;
+  uint64_t V;
+};
+
+struct ScoreParams {
+  TableView tab[2];      // 0 = title, 1 = body
+  const double* mag[2];
+  const double* sqd;     // [D] blend term for a shared topic vector, or NULL
+  const double* pr;      // [D][T] for per-query topic vectors
+  const double* probs;   // [n_q][T] when per-query
+  uint32_t T;
+  uint64_t D;
+  const uint64_t* kw_ptr;
+  const uint32_t* kw_terms;
+  const uint64_t* ph_ptr;
+  const uint32_t* ph_terms;
+  uint32_t n_q, n_slabs, k;
+  uint64_t slab_docs;    // multiple of kRange
+  uint32_t* part_doc;    // [n_q][n_slabs][k]
+  double* part_final;
+  double* part_pr;
+  uint32_t* part_count;  // [n_q][n_slabs]
+  unsigned long long* stats;  // [0] postings scanned, [1] docs matched
+};
+
+// Total order of results: FinalRank descending, ties by ascending doc id, NaN
+// last (util.go:48-54 with the arrival-order tie pinned).  Scores map to
+// unsigned keys whose integer order is the score order.
+__device__ __forceinline__ uint64_t score_key(double f) {
+  if (isnan(f)) return 0ull;
+  if (f == 0.0) f = 0.0;  // -0 == +0
+  const uint64_t b = (uint64_t)__double_as_longlong(f);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_score(uint64_t key) {
+  if (key == 0ull) return __longlong_as_double(0x7FF8000000000000ll);
+  const uint64_t b = (key >> 63) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+  return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ bool beats(uint64_t ka, uint32_t da, uint64_t kb, uint32_t db) {
+  return ka > kb || (ka == kb && da < db);
+}
+
+// first index in [lo, hi) with docs[i] >= target, galloping from lo
+__device__ __forceinline__ uint64_t gallop_lower_bound(const uint32_t* __restrict__ docs, uint64_t lo, uint64_t hi,
+                                                       uint64_t target) {
+  if (lo >= hi || docs[lo] >= target) return lo;
+  uint64_t step = 1, a = lo;  // docs[a] < target
+  while (a + step < hi && docs[a + step] < target) {
+    a += step;
+    step <<= 1;
+  }
+  uint64_t b = min(hi, a + step);  // answer in (a, b]
+  ++a;
+  while (a < b) {
+    const uint64_t mid = (a + b) >> 1;
+    if (docs[mid] < target) a = mid + 1; else b = mid;
+  }
+  return a;
+}
+
+struct Smem {
+  double acc[2][kRange];        // [0] TitleRank, [1] BodyRank sums of the sub-range
+  unsigned long long cand_key[kCand];
+  unsigned long long top_key[2][kMaxK];
+  unsigned long long cur[kMaxLists], end[kMaxLists], hi[kMaxLists];
+  uint32_t cand_doc[kCand];
+  uint32_t top_doc[2][kMaxK];
+  uint32_t bits[kRange / 32];
+  uint32_t n_cand, top_n, top_buf;
+  unsigned long long thr_key;
+  uint32_t thr_doc;
+};
+
+// Union of the running top-k and the candidate buffer -> new running top-k by
+// counting, for each element, how many others beat it (elements are distinct
+// in (key, doc), so ranks are a permutation).
+__device__ void merge_candidates(Smem& s, uint32_t k) {
+  const uint32_t nt = s.top_n, nc = s.n_cand, n = nt + nc;
+  const uint32_t ob = s.top_buf, nb = ob ^ 1;
+  for (uint32_t i = threadIdx.x; i < n; i += kT) {
+    const unsigned long long ki = i < nt ? s.top_key[ob][i] : s.cand_key[i - nt];
+    const uint32_t di = i < nt ? s.top_doc[ob][i] : s.cand_doc[i - nt];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < nt; ++j) rank += beats(s.top_key[ob][j], s.top_doc[ob][j], ki, di) ? 1u : 0u;
+    for (uint32_t j = 0; j < nc; ++j) rank += beats(s.cand_key[j], s.cand_doc[j], ki, di) ? 1u : 0u;
+    if (rank < k) {
+      s.top_key[nb][rank] = ki;
+      s.top_doc[nb][rank] = di;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s.top_n = min(k, n);
+    s.top_buf = nb;
+    s.n_cand = 0;
+    if (s.top_n == k) {
+      s.thr_key = s.top_key[nb][k - 1];
+      s.thr_doc = s.top_doc[nb][k - 1];
+    }
+  }
+  __syncthreads();
+}
+
+// phrase.go:53-109 for one table inside the current sub-range.  lists l0+2*i+tb
+// hold token i's narrowed posting range.  A doc gets ONE weight = fp32 sum of
+// the tokens' weights in phrase order iff every token has a posting in this
+// table and some position a of token 0 has a + i among token i's positions
+// (compared as (pos_i - float32(i)) == pos_0, phrase.go:144-146, util.go:185).
+__device__ void apply_phrase(const ScoreParams& p, Smem& s, int tb, uint32_t l0, uint32_t L, uint64_t d0,
+                             unsigned long long& n_postings) {
+  const TableView& tv = p.tab[tb];
+  uint32_t drv = 0;
+  unsigned long long best = ~0ull;
+  for (uint32_t i = 0; i < L; ++i) {
+    const uint32_t l = l0 + 2 * i + tb;
+    const unsigned long long len = s.hi[l] - s.cur[l];
+    if (len == 0) return;  // a token without postings here: nothing can match (uniform across the CTA)
+    if (len < best) {
+      best = len;
+      drv = i;
+    }
+  }
+  const uint32_t ld = l0 + 2 * drv + tb;
+  for (unsigned long long q = s.cur[ld] + threadIdx.x; q < s.hi[ld]; q += kT) {
+    const uint32_t doc = tv.doc_ids[q];
+    unsigned long long pi[kMaxPh];
+    bool all = true;
+    for (uint32_t i = 0; i < L && all; ++i) {
+      if (i == drv) {
+        pi[i] = q;
+        continue;
+      }
+      const uint32_t l = l0 + 2 * i + tb;
+      unsigned long long a = s.cur[l], b = s.hi[l];
+      while (a < b) {
+        const unsigned long long mid = (a + b) >> 1;
+        if (tv.doc_ids[mid] < doc) a = mid + 1; else b = mid;
+      }
+      if (a < s.hi[l] && tv.doc_ids[a] == doc) pi[i] = a; else all = false;
+    }
+    n_postings += L;
+    if (!all) continue;
+    bool hit = false;
+    if (tv.pos_ptr) {
+      const unsigned long long a0 = tv.pos_ptr[pi[0]], a1 = tv.pos_ptr[pi[0] + 1];
+      for (unsigned long long x = a0; x < a1 && !hit; ++x) {
+        const float a = __fadd_rn(tv.pos[x], -0.0f);
+        bool ok = true;
+        for (uint32_t i = 1; i < L && ok; ++i) {
+          const float shift = (float)(uint8_t)i;
+          bool found = false;
+          for (unsigned long long y = tv.pos_ptr[pi[i]]; y < tv.pos_ptr[pi[i] + 1] && !found; ++y)
+            found = __fadd_rn(tv.pos[y], -shift) == a;
+          ok = found;
+        }
+        hit = ok;
+      }
+    }
+    if (!hit) continue;
+    float sum = 0.0f;  // phrase.go:59,69,83: float32 running sum in token order
+    for (uint32_t i = 0; i < L; ++i) sum = __fadd_rn(sum, tv.w[pi[i]]);
+    const uint32_t slot = (uint32_t)(doc - d0);
+    s.acc[tb][slot] = __dadd_rn(s.acc[tb][slot], (double)sum);
+    atomicOr(&s.bits[slot >> 5], 1u << (slot & 31));
+  }
+}
+
+__global__ void __launch_bounds__(kT) k_score(ScoreParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  const uint32_t q = blockIdx.x % p.n_q, slab = blockIdx.x / p.n_q;  // slab-major launch order
+  const uint32_t tid = threadIdx.x;
+  const uint64_t kb = p.kw_ptr[q], ke = p.kw_ptr[q + 1];
+  const uint64_t pb = p.ph_ptr ? p.ph_ptr[q] : 0, pe = p.ph_ptr ? p.ph_ptr[q + 1] : 0;
+  const uint32_t n_kw = (uint32_t)(ke - kb);
+  uint32_t n_ph = (uint32_t)(pe - pb);
+  const uint32_t q_len = n_kw + n_ph;            // main_retrieve.go:90
+  if (n_ph > kMaxPh) n_ph = 0;                   // host rejects 33..256; >256 can never match (uint8 TermPos)
+  const uint32_t n_tok = n_kw + n_ph, n_lists = 2 * n_tok;
+  const uint64_t slab_lo = (uint64_t)slab * p.slab_docs;
+  const uint64_t slab_hi = min(p.D, slab_lo + p.slab_docs);
+  const uint32_t k = p.k;
+
+  for (uint32_t i = tid; i < kRange; i += kT) {
+    s.acc[0][i] = 0.0;
+    s.acc[1][i] = 0.0;
+  }
+  for (uint32_t i = tid; i < kRange / 32; i += kT) s.bits[i] = 0;
+  if (tid == 0) {
+    s.n_cand = 0;
+    s.top_n = 0;
+    s.top_buf = 0;
+    s.thr_key = 0;
+    s.thr_doc = kNoDoc;
+  }
+  // narrow every list to the slab
+  for (uint32_t l = tid; l < n_lists; l += kT) {
+    const uint32_t tok = l >> 1, tb = l & 1;
+    const uint32_t term = tok < n_kw ? p.kw_terms[kb + tok] : p.ph_terms[pb + (tok - n_kw)];
+    const TableView& tv = p.tab[tb];
+    unsigned long long a = 0, b = 0;
+    if (tv.term_ptr && term < tv.V) {  // unknown term => empty row (main_retrieve.go:193,218)
+      a = tv.term_ptr[term];
+      b = tv.term_ptr[term + 1];
+    }
+    a = gallop_lower_bound(tv.doc_ids, a, b, slab_lo);
+    s.cur[l] = a;
+    s.end[l] = gallop_lower_bound(tv.doc_ids, a, b, slab_hi);
+  }
+  __syncthreads();
+
+  const double qm = sqrt((double)q_len);  // get_metadata.go:53
+  unsigned long long n_postings = 0, n_matched = 0;
+
+  for (uint64_t d0 = slab_lo; d0 < slab_hi; d0 += kRange) {
+    const uint64_t d1 = min(slab_hi, d0 + kRange);
+    for (uint32_t l = tid; l < n_lists; l += kT)
+      s.hi[l] = gallop_lower_bound(p.tab[l & 1].doc_ids, s.cur[l], s.end[l], d1);
+    __syncthreads();
+
+    // keyword tokens in query order (duplicates count again)
+    bool any = false;
+    for (uint32_t i = 0; i < n_kw; ++i) {
+      const unsigned long long t0 = s.cur[2 * i], t1 = s.hi[2 * i], b0 = s.cur[2 * i + 1], b1 = s.hi[2 * i + 1];
+      if (t1 == t0 && b1 == b0) continue;
+      any = true;
+      for (unsigned long long x = b0 + tid; x < b1; x += kT) {
+        const uint32_t slot = (uint32_t)(p.tab[1].doc_ids[x] - d0);
+        s.acc[1][slot] = __dadd_rn(s.acc[1][slot], (double)p.tab[1].w[x]);
+        atomicOr(&s.bits[slot >> 5], 1u << (slot & 31));
+      }
+      for (unsigned long long x = t0 + tid; x < t1; x += kT) {
+        const uint32_t slot = (uint32_t)(p.tab[0].doc_ids[x] - d0);
+        s.acc[0][slot] = __dadd_rn(s.acc[0][slot], (double)p.tab[0].w[x]);
+        atomicOr(&s.bits[slot >> 5], 1u << (slot & 31));
+      }
+      if (tid == 0) n_postings += (t1 - t0) + (b1 - b0);
+      __syncthreads();
+    }
+    // the phrase's weight is appended after the keyword weights (main_retrieve.go:73-78)
+    if (n_ph) {
+      bool ph_any = false;
+      for (uint32_t i = 0; i < 2 * n_ph; ++i) ph_any |= s.hi[2 * n_kw + i] != s.cur[2 * n_kw + i];
+      if (ph_any) {
+        any = true;
+        apply_phrase(p, s, 1, 2 * n_kw, n_ph, d0, n_postings);
+        apply_phrase(p, s, 0, 2 * n_kw, n_ph, d0, n_postings);
+        __syncthreads();
+      }
+    }
+
+    if (any) {
+      const uint32_t n_slots = (uint32_t)(d1 - d0);
+      for (uint32_t c0 = 0; c0 < n_slots; c0 += kCand) {
+        for (uint32_t i = tid; i < kCand; i += kT) {
+          const uint32_t slot = c0 + i;
+          if (slot >= n_slots || !((s.bits[slot >> 5] >> (slot & 31)) & 1u)) continue;
+          const uint64_t doc = d0 + slot;
+          const double tr = s.acc[0][slot], br = s.acc[1][slot];
+          s.acc[0][slot] = 0.0;
+          s.acc[1][slot] = 0.0;
+          ++n_matched;
+          double body = __ddiv_rn(br, __dmul_rn(p.mag[1][doc], qm));   // get_metadata.go:57
+          double title = __ddiv_rn(tr, __dmul_rn(p.mag[0][doc], qm));  // :58
+          if (isnan(body)) body = 0.0;                                 // :61-66
+          if (isnan(title)) title = 0.0;
+          double sqd = 0.0;  // :39-42
+          if (p.sqd) {
+            sqd = p.sqd[doc];
+          } else if (p.probs) {
+            const double* pr = p.pr + doc * p.T;
+            const double* pq = p.probs + (uint64_t)q * p.T;
+            for (uint32_t t = 0; t < p.T; ++t) sqd = __dadd_rn(sqd, __dmul_rn(pq[t], pr[t]));
+          }
+          // (0.33*sqd + 0.38*Title + 0.29*Body) * 100.0, left to right, no fusing (:69)
+          const double fin = __dmul_rn(
+              __dadd_rn(__dadd_rn(__dmul_rn(0.33, sqd), __dmul_rn(0.38, title)), __dmul_rn(0.29, body)), 100.0);
+          const unsigned long long key = score_key(fin);
+          if (s.top_n < k || beats(key, (uint32_t)doc, s.thr_key, s.thr_doc)) {
+            const uint32_t j = atomicAdd(&s.n_cand, 1u);
+            s.cand_key[j] = key;
+            s.cand_doc[j] = (uint32_t)doc;
+          }
+        }
+        __syncthreads();
+        if (s.n_cand) merge_candidates(s, k);
+      }
+      for (uint32_t i = tid; i < kRange / 32; i += kT) s.bits[i] = 0;
+    }
+    for (uint32_t l = tid; l < n_lists; l += kT) s.cur[l] = s.hi[l];
+    __syncthreads();
+  }
+
+  // this slab's list
+  const size_t base = ((size_t)q * p.n_slabs + slab) * k;
+  const uint32_t tb = s.top_buf, tn = s.top_n;
+  for (uint32_t j = tid; j < k; j += kT) {
+    if (j < tn) {
+      const uint32_t doc = s.top_doc[tb][j];
+      double sqd = 0.0;
+      if (p.sqd) {
+        sqd = p.sqd[doc];
+      } else if (p.probs) {
+        const double* pr = p.pr + (uint64_t)doc * p.T;
+        const double* pq = p.probs + (uint64_t)q * p.T;
+        for (uint32_t t = 0; t < p.T; ++t) sqd = __dadd_rn(sqd, __dmul_rn(pq[t], pr[t]));
+      }
+      p.part_doc[base + j] = doc;
+      p.part_final[base + j] = key_score(s.top_key[tb][j]);
+      p.part_pr[base + j] = sqd;
+    } else {
+      p.part_doc[base + j] = kNoDoc;
+      p.part_final[base + j] = 0.0;
+      p.part_pr[base + j] = 0.0;
+    }
+  }
+  if (tid == 0) p.part_count[(size_t)q * p.n_slabs + slab] = tn;
+  // stats: warp-reduce then one atomic per warp
+  for (int o = 16; o; o >>= 1) {
+    n_postings += __shfl_xor_sync(0xFFFFFFFFu, n_postings, o);
+    n_matched += __shfl_xor_sync(0xFFFFFFFFu, n_matched, o);
+  }
+  if ((tid & 31) == 0) {
+    if (n_postings) atomicAdd(p.stats, n_postings);
+    if (n_matched) atomicAdd(p.stats + 1, n_matched);
+  }
+}
+
+// Merge n_lists lists of up to k results per query into one, same total order.
+// in_*: [n_q][n_lists][k] (list_major == 0) or [n_lists][n_q][k] (list_major == 1).
+constexpr int kMergeMax = 4096;
+__global__ void __launch_bounds__(kT) k_merge(uint32_t n_lists, uint32_t k, uint32_t n_q, int list_major,
+                                              const uint32_t* __restrict__ in_doc, const double* __restrict__ in_final,
+                                              const double* __restrict__ in_pr, const uint32_t* __restrict__ in_count,
+                                              uint32_t* __restrict__ out_doc, double* __restrict__ out_final,
+                                              double* __restrict__ out_pr, uint32_t* __restrict__ out_count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_raw);
+  uint32_t* doc = reinterpret_cast<uint32_t*>(key + (size_t)n_lists * k);
+  __shared__ uint32_t total;
+  const uint32_t q = blockIdx.x, n = n_lists * k;
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n; i += kT) {
+    const uint32_t l = i / k, j = i % k;
+    const size_t src = list_major ? ((size_t)l * n_q + q) * k + j : ((size_t)q * n_lists + l) * k + j;
+    const uint32_t cnt = in_count[list_major ? (size_t)l * n_q + q : (size_t)q * n_lists + l];
+    const bool ok = j < cnt && in_doc[src] != kNoDoc;
+    key[i] = ok ? score_key(in_final[src]) : 0ull;
+    doc[i] = ok ? in_doc[src] : kNoDoc;
+    if (ok) atomicAdd(&total, 1u);
+  }
+  for (uint32_t j = threadIdx.x; j < k; j += kT) {
+    out_doc[(size_t)q * k + j] = kNoDoc;
+    out_final[(size_t)q * k + j] = 0.0;
+    out_pr[(size_t)q * k + j] = 0.0;
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n; i += kT) {
+    if (doc[i] == kNoDoc) continue;
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < n; ++j) rank += (doc[j] != kNoDoc && beats(key[j], doc[j], key[i], doc[i])) ? 1u : 0u;
+    if (rank < k) {
+      const uint32_t l = i / k, jj = i % k;
+      const size_t src = list_major ? ((size_t)l * n_q + q) * k + jj : ((size_t)q * n_lists + l) * k + jj;
+      out_doc[(size_t)q * k + rank] = doc[i];
+      out_final[(size_t)q * k + rank] = in_final[src];
+      out_pr[(size_t)q * k + rank] = in_pr[src];
+    }
+  }
+  if (threadIdx.x == 0) out_count[q] = min(total, k);
+}
+
+// sqd[d] = sum_t probs[t] * pr[d][t], ascending t, separately rounded (get_metadata.go:39-42)
+__global__ void k_sqd(const double* __restrict__ pr, const double* __restrict__ probs, uint32_t T, uint64_t D,
+                      double* __restrict__ sqd) {
+  const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  double acc = 0.0;
+  for (uint32_t t = 0; t < T; ++t) acc = __dadd_rn(acc, __dmul_rn(probs[t], pr[d * T + t]));
+  sqd[d] = acc;
+}
+
+TableView view_of(const TableState& tb) {
+  TableView v{};
+  if (!tb.loaded) return v;
+  v.term_ptr = tb.term_ptr.p;
+  v.doc_ids = tb.doc_ids.p;
+  v.w = tb.w.p;
+  v.pos_ptr = tb.has_pos ? tb.pos_ptr.p : nullptr;
+  v.pos = tb.has_pos ? tb.pos.p : nullptr;
+  v.V = tb.V;
+  return v;
+}
+
+}  // namespace
+
+extern "C" {
+
+SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, const uint32_t* kw_terms,
+                          const uint64_t* ph_ptr, const uint32_t* ph_terms, const double* topic_probs,
+                          int32_t probs_per_query, uint32_t k, uint32_t* out_doc, double* out_final, double* out_pr,
+                          uint32_t* out_count) {
+  SS_REQUIRE(e, SS_ERR_INVALID, "ss_score_batch: engine is NULL");
+  SS_REQUIRE(n_q == 0 || (kw_ptr && out_doc && out_final && out_pr && out_count), SS_ERR_INVALID,
+             "ss_score_batch: NULL argument");
+  SS_REQUIRE(k >= 1 && k <= (uint32_t)kMaxK, SS_ERR_INVALID, "ss_score_batch: k = %u, supported 1..%d", k, kMaxK);
+  SS_REQUIRE(n_q < 0x7FFFFFFFull, SS_ERR_INVALID, "ss_score_batch: batch too large");
+  if (n_q == 0) return SS_OK;
+  const uint64_t n_kw = kw_ptr[n_q], n_ph = ph_ptr ? ph_ptr[n_q] : 0;
+  SS_REQUIRE((n_kw == 0 || kw_terms) && (n_ph == 0 || ph_terms), SS_ERR_INVALID, "ss_score_batch: NULL terms");
+  for (uint64_t q = 0; q < n_q; ++q) {
+    SS_REQUIRE(kw_ptr[q] <= kw_ptr[q + 1] && kw_ptr[q + 1] - kw_ptr[q] <= (uint64_t)kMaxKw, SS_ERR_INVALID,
+               "ss_score_batch: query %llu has a bad keyword range (max %d tokens)", (unsigned long long)q, kMaxKw);
+    if (ph_ptr) {
+      SS_REQUIRE(ph_ptr[q] <= ph_ptr[q + 1], SS_ERR_INVALID, "ss_score_batch: ph_ptr not monotone");
+      const uint64_t L = ph_ptr[q + 1] - ph_ptr[q];
+      // > 256 tokens can never match (uint8 TermPos, phrase.go:115); 33..256 would, but is not supported
+      SS_REQUIRE(L <= (uint64_t)kMaxPh || L > 256, SS_ERR_INVALID,
+                 "ss_score_batch: query %llu has a %llu-token phrase (max %d)", (unsigned long long)q,
+                 (unsigned long long)L, kMaxPh);
+    }
+  }
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  IndexState* ix = e->idx;
+  SS_REQUIRE(ix && (ix->tab[0].loaded || ix->tab[1].loaded), SS_ERR_STATE, "ss_score_batch: no index loaded");
+  for (int tb = 0; tb < 2; ++tb)
+    SS_REQUIRE(!ix->tab[tb].loaded || ix->tab[tb].has_mag, SS_ERR_STATE,
+               "ss_score_batch: table %d has no doc norms (ss_term_weights / ss_set_doc_norms)", tb);
+  const uint64_t D = ix->D;
+  const bool blend = topic_probs != nullptr;
+  if (blend) {
+    SS_REQUIRE(ix->pr.p && ix->T > 0, SS_ERR_STATE, "ss_score_batch: topic_probs given but no PageRank set");
+    SS_REQUIRE(ix->pr_docs >= D, SS_ERR_STATE, "ss_score_batch: PageRank covers %llu docs, index has %llu",
+               (unsigned long long)ix->pr_docs, (unsigned long long)D);
+  }
+  cudaStream_t st = e->stream;
+  const bool timing = (e->flags & SS_FLAG_TIMING) != 0;
+  uint32_t launches = 0;
+
+  // a table that was never loaded behaves as an empty one with zero norms
+  ss::DevBuf<double> zero_mag;
+  for (int tb = 0; tb < 2; ++tb)
+    if (!ix->tab[tb].loaded && zero_mag.n == 0) {
+      SS_TRY(zero_mag.alloc(D));
+      SS_CUDA(cudaMemsetAsync(zero_mag.p, 0, std::max<uint64_t>(D, 1) * 8, st));
+    }
+
+  ss::DevBuf<uint64_t> d_kw_ptr, d_ph_ptr;
+  ss::DevBuf<uint32_t> d_kw, d_ph;
+  ss::DevBuf<double> d_probs;
+  SS_TRY(d_kw_ptr.alloc(n_q + 1));
+  SS_TRY(d_kw.alloc(n_kw));
+  SS_CUDA(cudaMemcpyAsync(d_kw_ptr.p, kw_ptr, (n_q + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (n_kw) SS_CUDA(cudaMemcpyAsync(d_kw.p, kw_terms, n_kw * 4, cudaMemcpyHostToDevice, st));
+  if (ph_ptr) {
+    SS_TRY(d_ph_ptr.alloc(n_q + 1));
+    SS_TRY(d_ph.alloc(n_ph));
+    SS_CUDA(cudaMemcpyAsync(d_ph_ptr.p, ph_ptr, (n_q + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_ph) SS_CUDA(cudaMemcpyAsync(d_ph.p, ph_terms, n_ph * 4, cudaMemcpyHostToDevice, st));
+  }
+
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  if (timing)
+    for (auto& x : ev) SS_CUDA(cudaEventCreate(&x));
+  struct EvGuard {
+    cudaEvent_t* ev;
+    ~EvGuard() {
+      for (int i = 0; i < 3; ++i)
+        if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+  } ev_guard{ev};
+  if (timing) SS_CUDA(cudaEventRecord(ev[0], st));
+
+  // blend term: one pass over forw[3] for a shared topic vector, cached across batches
+  const double* sqd_ptr = nullptr;
+  if (blend && !probs_per_query) {
+    std::vector<double> h(topic_probs, topic_probs + ix->T);
+    const bool same = ix->sqd_valid && ix->sqd_probs.size() == h.size() &&
+                      memcmp(ix->sqd_probs.data(), h.data(), h.size() * 8) == 0;
+    if (!same) {
+      SS_TRY(d_probs.alloc(ix->T));
+      SS_CUDA(cudaMemcpyAsync(d_probs.p, topic_probs, ix->T * 8, cudaMemcpyHostToDevice, st));
+      if (ix->sqd.n != std::max<uint64_t>(D, 1)) SS_TRY(ix->sqd.alloc(D));
+      if (D) k_sqd<<<ss::div_up(D, 256), 256, 0, st>>>(ix->pr.p, d_probs.p, ix->T, D, ix->sqd.p);
+      ++launches;
+      ix->sqd_probs = h;
+      ix->sqd_valid = true;
+    }
+    sqd_ptr = ix->sqd.p;
+  } else if (blend) {
+    SS_TRY(d_probs.alloc(n_q * ix->T));
+    SS_CUDA(cudaMemcpyAsync(d_probs.p, topic_probs, n_q * ix->T * 8, cudaMemcpyHostToDevice, st));
+  }
+
+  // slabs: enough CTAs to fill the machine, index slice per slab around the L2 size,
+  // and n_slabs * k small enough for the merge kernel
+  const uint64_t n_sub = std::max<uint64_t>(1, (D + kRange - 1) / kRange);
+  const uint64_t index_bytes = (ix->tab[0].P + ix->tab[1].P) * 8;
+  uint64_t n_slabs = std::max<uint64_t>(1, (index_bytes + (64ull << 20) - 1) / (64ull << 20));
+  const uint64_t want_ctas = (uint64_t)e->sm_count * 16;
+  n_slabs = std::max(n_slabs, (want_ctas + n_q - 1) / n_q);
+  n_slabs = std::min<uint64_t>(n_slabs, n_sub);
+  n_slabs = std::min<uint64_t>(n_slabs, std::max<uint64_t>(1, (uint64_t)kMergeMax / k));
+  const uint64_t sub_per_slab = (n_sub + n_slabs - 1) / n_slabs;
+  n_slabs = (n_sub + sub_per_slab - 1) / sub_per_slab;
+  SS_REQUIRE(n_q * n_slabs < 0x7FFFFFFFull, SS_ERR_INVALID, "ss_score_batch: batch too large; split it");
+
+  ss::DevBuf<uint32_t> part_doc, part_count, d_out_doc, d_out_count;
+  ss::DevBuf<double> part_final, part_pr, d_out_final, d_out_pr;
+  ss::DevBuf<unsigned long long> d_stats;
+  SS_TRY(part_doc.alloc(n_q * n_slabs * k));
+  SS_TRY(part_final.alloc(n_q * n_slabs * k));
+  SS_TRY(part_pr.alloc(n_q * n_slabs * k));
+  SS_TRY(part_count.alloc(n_q * n_slabs));
+  SS_TRY(d_out_doc.alloc(n_q * k));
+  SS_TRY(d_out_final.alloc(n_q * k));
+  SS_TRY(d_out_pr.alloc(n_q * k));
+  SS_TRY(d_out_count.alloc(n_q));
+  SS_TRY(d_stats.alloc(2));
+  SS_CUDA(cudaMemsetAsync(d_stats.p, 0, 16, st));
+
+  ScoreParams p{};
+  p.tab[0] = view_of(ix->tab[0]);
+  p.tab[1] = view_of(ix->tab[1]);
+  p.mag[0] = ix->tab[0].loaded ? ix->tab[0].mag.p : zero_mag.p;
+  p.mag[1] = ix->tab[1].loaded ? ix->tab[1].mag.p : zero_mag.p;
+  p.sqd = sqd_ptr;
+  p.pr = (blend && probs_per_query) ? ix->pr.p : nullptr;
+  p.probs = (blend && probs_per_query) ? d_probs.p : nullptr;
+  p.T = ix->T;
+  p.D = D;
+  p.kw_ptr = d_kw_ptr.p;
+  p.kw_terms = d_kw.p;
+  p.ph_ptr = ph_ptr ? d_ph_ptr.p : nullptr;
+  p.ph_terms = d_ph.p;
+  p.n_q = (uint32_t)n_q;
+  p.n_slabs = (uint32_t)n_slabs;
+  p.k = k;
+  p.slab_docs = sub_per_slab * kRange;
+  p.part_doc = part_doc.p;
+  p.part_final = part_final.p;
+  p.part_pr = part_pr.p;
+  p.part_count = part_count.p;
+  p.stats = d_stats.p;
+
+  SS_CUDA(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  SS_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeMax * 12));
+  if (timing) SS_CUDA(cudaEventRecord(ev[1], st));
+  k_score<<<(unsigned)(n_q * n_slabs), kT, sizeof(Smem), st>>>(p);
+  if (timing) SS_CUDA(cudaEventRecord(ev[2], st));
+  k_merge<<<(unsigned)n_q, kT, (size_t)n_slabs * k * 12, st>>>((uint32_t)n_slabs, k, (uint32_t)n_q, 0, part_doc.p,
+                                                              part_final.p, part_pr.p, part_count.p, d_out_doc.p,
+                                                              d_out_final.p, d_out_pr.p, d_out_count.p);
+  launches += 2;
+  cudaEvent_t ev_end = nullptr;
+  if (timing) {
+    SS_CUDA(cudaEventCreate(&ev_end));
+    SS_CUDA(cudaEventRecord(ev_end, st));
+  }
+  SS_CUDA(cudaMemcpyAsync(out_doc, d_out_doc.p, n_q * k * 4, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(out_final, d_out_final.p, n_q * k * 8, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(out_pr, d_out_pr.p, n_q * k * 8, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(out_count, d_out_count.p, n_q * 4, cudaMemcpyDeviceToHost, st));
+  unsigned long long h_stats[2] = {0, 0};
+  SS_CUDA(cudaMemcpyAsync(h_stats, d_stats.p, 16, cudaMemcpyDeviceToHost, st));
+  cudaError_t sync_err = cudaStreamSynchronize(st);
+  if (sync_err == cudaSuccess) sync_err = cudaGetLastError();
+  if (sync_err != cudaSuccess) {
+    if (ev_end) cudaEventDestroy(ev_end);
+    ss::set_error("ss_score_batch: %s", cudaGetErrorString(sync_err));
+    return SS_ERR_CUDA;
+  }
+  ix->stats.postings_scanned = h_stats[0];
+  ix->stats.docs_matched = h_stats[1];
+  // SURVEY.md §8(d) B_q summed: 8 B per posting, per matched doc two norms + the blend
+  // input this implementation reads (8 B cached sqd or the 8T-byte forw[3] row), 12 B per result
+  const uint64_t per_doc = 16 + (blend ? (probs_per_query ? 8ull * ix->T : 8ull) : 0ull);
+  ix->stats.algorithmic_bytes = 8ull * h_stats[0] + per_doc * h_stats[1] + 12ull * k * n_q;
+  ix->stats.launches = launches;
+  if (timing) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev[0], ev_end);
+    ix->stats.kernel_ms = ms;
+    cudaEventElapsedTime(&ms, ev[1], ev[2]);
+    ix->stats.score_kernel_ms = ms;
+  }
+  if (ev_end) cudaEventDestroy(ev_end);
+  return SS_OK;
+}
+
+SS_API int ss_merge_topk(ss_engine* e, uint32_t n_lists, uint64_t n_q, uint32_t k, const uint32_t* docs,
+                         const double* finals, const double* prs, const uint32_t* counts, uint32_t* out_doc,
+                         double* out_final, double* out_pr, uint32_t* out_count) {
+  SS_REQUIRE(e, SS_ERR_INVALID, "ss_merge_topk: engine is NULL");
+  SS_REQUIRE(n_q == 0 || (docs && finals && prs && counts && out_doc && out_final && out_pr && out_count),
+             SS_ERR_INVALID, "ss_merge_topk: NULL argument");
+  SS_REQUIRE(n_lists >= 1 && k >= 1 && (uint64_t)n_lists * k <= (uint64_t)kMergeMax, SS_ERR_INVALID,
+             "ss_merge_topk: n_lists * k = %llu, max %d", (unsigned long long)n_lists * k, kMergeMax);
+  if (n_q == 0) return SS_OK;
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  cudaStream_t st = e->stream;
+  const size_t n = (size_t)n_lists * n_q * k;
+  ss::DevBuf<uint32_t> d_doc, d_cnt, o_doc, o_cnt;
+  ss::DevBuf<double> d_fin, d_pr, o_fin, o_pr;
+  SS_TRY(d_doc.alloc(n));
+  SS_TRY(d_fin.alloc(n));
+  SS_TRY(d_pr.alloc(n));
+  SS_TRY(d_cnt.alloc((size_t)n_lists * n_q));
+  SS_TRY(o_doc.alloc(n_q * k));
+  SS_TRY(o_fin.alloc(n_q * k));
+  SS_TRY(o_pr.alloc(n_q * k));
+  SS_TRY(o_cnt.alloc(n_q));
+  SS_CUDA(cudaMemcpyAsync(d_doc.p, docs, n * 4, cudaMemcpyHostToDevice, st));
+  SS_CUDA(cudaMemcpyAsync(d_fin.p, finals, n * 8, cudaMemcpyHostToDevice, st));
+  SS_CUDA(cudaMemcpyAsync(d_pr.p, prs, n * 8, cudaMemcpyHostToDevice, st));
+  SS_CUDA(cudaMemcpyAsync(d_cnt.p, counts, (size_t)n_lists * n_q * 4, cudaMemcpyHostToDevice, st));
+  SS_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeMax * 12));
+  k_merge<<<(unsigned)n_q, kT, (size_t)n_lists * k * 12, st>>>(n_lists, k, (uint32_t)n_q, 1, d_doc.p, d_fin.p, d_pr.p,
+                                                              d_cnt.p, o_doc.p, o_fin.p, o_pr.p, o_cnt.p);
+  SS_CUDA(cudaMemcpyAsync(out_doc, o_doc.p, n_q * k * 4, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(out_final, o_fin.p, n_q * k * 8, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(out_pr, o_pr.p, n_q * k * 8, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(out_count, o_cnt.p, n_q * 4, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaStreamSynchronize(st));
+  SS_CUDA(cudaGetLastError());
+  return SS_OK;
+}
+
+SS_API int ss_score_get_stats(ss_engine* e, ss_score_stats* out) {
+  SS_REQUIRE(e && out, SS_ERR_INVALID, "ss_score_get_stats: NULL argument");
+  std::lock_guard<std::mutex> lock(e->mu);
+  SS_REQUIRE(e->idx, SS_ERR_STATE, "ss_score_get_stats: no index loaded");
+  *out = e->idx->stats;
+  return SS_OK;
+}
+
+}  // extern "C"

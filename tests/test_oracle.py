@@ -9,6 +9,7 @@ import pytest
 
 from oracle import loader as O
 from spaghettisearch_b200 import synth
+from tests.fixtures import tiny_index as _tiny_index
 
 KATS = json.loads((Path(__file__).parent / "golden" / "kats.json").read_text())
 
@@ -83,31 +84,6 @@ def test_kat_sc1(built):
     assert (pr[0] == 0).all() and (docs[0, 3:] == 0xFFFFFFFF).all()
     # SURVEY.md §8(c) seed values
     assert final[0, :3].tolist() == [47.376154339498676, 27.5118156434649, 3.371181523570759]
-
-
-def _tiny_index():
-    # docs 0..5, terms 0..3; body with positions, title with positions incl. the -100 sentinel
-    body = {0: {0: (0.5, [1, 7]), 1: (1.0, [2]), 4: (0.25, [9])},
-            1: {0: (1.0, [2, 30]), 1: (0.5, [5]), 2: (1.0, [0])},
-            2: {0: (0.75, [3]), 3: (1.0, [4])},
-            3: {5: (1.0, [])}}
-    title = {0: {1: (1.0, [-100]), 2: (0.5, [0])},
-             1: {2: (1.0, [1]), 3: (1.0, [-100])},
-             2: {0: (1.0, [-100]), 1: (0.5, [-100])}}
-
-    def csc(tab, n_terms):
-        ptr, docs, tf, pp, pos = [0], [], [], [0], []
-        for t in range(n_terms):
-            for d in sorted(tab.get(t, {})):
-                docs.append(d)
-                tf.append(tab[t][d][0])
-                pos.extend(tab[t][d][1])
-                pp.append(len(pos))
-            ptr.append(len(docs))
-        return (np.array(ptr, np.uint64), np.array(docs, np.uint32), np.array(tf, np.float32),
-                np.array(pp, np.uint64), np.array(pos, np.float32))
-
-    return csc(title, 4), csc(body, 4), 6
 
 
 def _weighted(built, total_docs=6.0):
