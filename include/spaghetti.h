@@ -63,6 +63,9 @@ SS_API int ss_version(void);
 SS_API int ss_create(const ss_config* cfg, ss_engine** out);
 SS_API void ss_destroy(ss_engine* e);
 SS_API const char* ss_last_error(void);
+/* The engine's CUDA stream (cudaStream_t) so that a harness can bracket calls
+ * with its own events; all of the engine's kernels and copies run on it. */
+SS_API void* ss_stream_handle(ss_engine* e);
 
 /* ---- multi-GPU (one engine per GPU) -----------------------
  * ss_comm_unique_id: 128-byte NCCL id created by rank 0 and passed to every
@@ -98,6 +101,7 @@ SS_API int ss_pagerank_fetch(ss_engine* e, uint64_t row_lo, uint64_t row_hi, dou
 
 typedef struct ss_pagerank_stats {
   uint64_t n_nodes, n_edges;   /* global */
+  uint64_t row_lo;             /* first destination row owned by this rank */
   uint64_t local_rows, local_edges; /* this rank's partition */
   uint32_t sweeps;             /* sweeps of the last ss_pagerank */
   uint32_t launches;           /* kernels launched by the last ss_pagerank */

@@ -51,6 +51,12 @@ def lib():
                                            C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
                                            C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         L.oracle_pagerank_fair.restype = C.c_int
+        L.oracle_csc_build.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_csc_build.restype = C.c_int
+        L.oracle_pagerank_fair_csc.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                               C.c_double, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32,
+                                               C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        L.oracle_pagerank_fair_csc.restype = C.c_int
         L.oracle_term_weights.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_double, C.c_void_p, C.c_void_p]
         L.oracle_term_weights.restype = C.c_int
@@ -117,6 +123,32 @@ def pagerank_fair(row_ptr, col_idx, damping, eps, num_pages, max_iters=0, fixed_
     rc = lib().oracle_pagerank_fair(n, _p(row_ptr), _p(col_idx), damping, eps, t, _p(num_pages),
                                     max_iters, fixed_iters, n_threads, _p(rank), _p(iters),
                                     C.byref(secs))
+    assert rc == 0
+    return rank, iters, secs.value
+
+
+def csc_build(row_ptr, col_idx):
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint64)
+    col_idx = np.ascontiguousarray(col_idx, dtype=np.uint32)
+    n = len(row_ptr) - 1
+    in_ptr = np.zeros(n + 1, dtype=np.uint64)
+    in_src = np.zeros(max(1, len(col_idx)), dtype=np.uint32)
+    assert lib().oracle_csc_build(n, _p(row_ptr), _p(col_idx), _p(in_ptr), _p(in_src)) == 0
+    return in_ptr, in_src
+
+
+def pagerank_fair_csc(row_ptr, in_ptr, in_src, damping, eps, num_pages, max_iters=0, fixed_iters=0,
+                      n_threads=0, want_rank=True):
+    """Fair CPU arm on a prebuilt in-edge CSC -> (rank or None, iters, seconds in the sweeps)."""
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint64)
+    num_pages = np.ascontiguousarray(num_pages, dtype=np.int64)
+    n, t = len(row_ptr) - 1, len(num_pages)
+    rank = np.zeros((n, t), dtype=np.float64) if want_rank else None
+    iters = np.zeros(t, dtype=np.uint32)
+    secs = C.c_double(0)
+    rc = lib().oracle_pagerank_fair_csc(n, _p(row_ptr), _p(in_ptr), _p(in_src), damping, eps, t,
+                                        _p(num_pages), max_iters, fixed_iters, n_threads, _p(rank),
+                                        _p(iters), C.byref(secs))
     assert rc == 0
     return rank, iters, secs.value
 

@@ -184,30 +184,34 @@ extern "C" int oracle_pagerank_faithful(uint64_t n_nodes, const uint64_t* row_pt
   return 0;
 }
 
-extern "C" int oracle_pagerank_fair(uint64_t n_nodes, const uint64_t* row_ptr,
-                                    const uint32_t* col_idx, double damping, double eps,
-                                    uint32_t n_topics, const int64_t* num_pages,
-                                    uint32_t max_iters, uint32_t fixed_iters, int n_threads,
-                                    double* out_rank, uint32_t* out_iters,
-                                    double* sweep_seconds) {
+// in-edge CSC of the out-edge CSR (sources ascending within a row)
+extern "C" int oracle_csc_build(uint64_t n_nodes, const uint64_t* row_ptr, const uint32_t* col_idx,
+                                uint64_t* in_ptr, uint32_t* in_src) {
   const uint64_t N = n_nodes, E = row_ptr[N];
-  const uint32_t T = n_topics;
-  if (n_threads <= 0) n_threads = omp_get_max_threads();
-  // in-edge CSC (sources ascending within a row)
-  std::vector<uint64_t> in_ptr(N + 1, 0);
+  for (uint64_t v = 0; v <= N; ++v) in_ptr[v] = 0;
   for (uint64_t i = 0; i < E; ++i) in_ptr[col_idx[i] + 1]++;
   for (uint64_t v = 0; v < N; ++v) in_ptr[v + 1] += in_ptr[v];
-  std::vector<uint32_t> in_src(E ? E : 1);
-  {
-    std::vector<uint64_t> fill(in_ptr.begin(), in_ptr.end() - 1);
-    for (uint64_t u = 0; u < N; ++u)
-      for (uint64_t i = row_ptr[u]; i < row_ptr[u + 1]; ++i) in_src[fill[col_idx[i]]++] = (uint32_t)u;
-  }
+  std::vector<uint64_t> fill(in_ptr, in_ptr + N);
+  for (uint64_t u = 0; u < N; ++u)
+    for (uint64_t i = row_ptr[u]; i < row_ptr[u + 1]; ++i) in_src[fill[col_idx[i]]++] = (uint32_t)u;
+  return 0;
+}
+
+extern "C" int oracle_pagerank_fair_csc(uint64_t n_nodes, const uint64_t* row_ptr, const uint64_t* in_ptr,
+                                        const uint32_t* in_src, double damping, double eps,
+                                        uint32_t n_topics, const int64_t* num_pages,
+                                        uint32_t max_iters, uint32_t fixed_iters, int n_threads,
+                                        double* out_rank, uint32_t* out_iters,
+                                        double* sweep_seconds) {
+  const uint64_t N = n_nodes;
+  const uint32_t T = n_topics;
+  if (n_threads <= 0) n_threads = omp_get_max_threads();
   const double teleport = 1.0 - damping;
   std::vector<double> last(N * T), cur(N * T), contrib(N * T);
   std::vector<double> tot(T), change(T, std::numeric_limits<double>::max());
   std::vector<char> active(T, 1);
   std::vector<uint32_t> iters(T, 0);
+#pragma omp parallel for num_threads(n_threads) schedule(static)
   for (uint64_t v = 0; v < N; ++v)
     for (uint32_t t = 0; t < T; ++t) last[v * T + t] = 1.0 / (double)num_pages[t];
   auto t0 = std::chrono::steady_clock::now();
@@ -272,6 +276,21 @@ extern "C" int oracle_pagerank_fair(uint64_t n_nodes, const uint64_t* row_ptr,
   if (out_iters) memcpy(out_iters, iters.data(), T * sizeof(uint32_t));
   if (out_rank) memcpy(out_rank, last.data(), N * T * sizeof(double));
   return 0;
+}
+
+extern "C" int oracle_pagerank_fair(uint64_t n_nodes, const uint64_t* row_ptr,
+                                    const uint32_t* col_idx, double damping, double eps,
+                                    uint32_t n_topics, const int64_t* num_pages,
+                                    uint32_t max_iters, uint32_t fixed_iters, int n_threads,
+                                    double* out_rank, uint32_t* out_iters,
+                                    double* sweep_seconds) {
+  const uint64_t N = n_nodes, E = row_ptr[N];
+  std::vector<uint64_t> in_ptr(N + 1);
+  std::vector<uint32_t> in_src(E ? E : 1);
+  oracle_csc_build(N, row_ptr, col_idx, in_ptr.data(), in_src.data());
+  return oracle_pagerank_fair_csc(N, row_ptr, in_ptr.data(), in_src.data(), damping, eps, n_topics,
+                                  num_pages, max_iters, fixed_iters, n_threads, out_rank, out_iters,
+                                  sweep_seconds);
 }
 
 // ---------------------------------------------------------- term weights ----

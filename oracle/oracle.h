@@ -56,6 +56,16 @@ int oracle_pagerank_fair(uint64_t n_nodes, const uint64_t* row_ptr, const uint32
                          uint32_t max_iters, uint32_t fixed_iters, int n_threads,
                          double* out_rank, uint32_t* out_iters, double* sweep_seconds);
 
+/* The transpose on its own (so that a timing loop pays for it once) and the fair
+ * arm on a prebuilt CSC. in_ptr is [n_nodes+1], in_src is [n_edges]. */
+int oracle_csc_build(uint64_t n_nodes, const uint64_t* row_ptr, const uint32_t* col_idx,
+                     uint64_t* in_ptr, uint32_t* in_src);
+int oracle_pagerank_fair_csc(uint64_t n_nodes, const uint64_t* row_ptr, const uint64_t* in_ptr,
+                             const uint32_t* in_src, double damping, double eps, uint32_t n_topics,
+                             const int64_t* num_pages, uint32_t max_iters, uint32_t fixed_iters,
+                             int n_threads, double* out_rank, uint32_t* out_iters,
+                             double* sweep_seconds);
+
 /* ---- HP-2 offline: ranking/term_weighting.go:10-57 + saveMagnitude ---------
  * Term-major postings.  idf = float32(Log2(total_docs / df)), df = postings of
  * the term in THIS table; w = normTF * idf in fp32; mag[doc] += float64(w*w)

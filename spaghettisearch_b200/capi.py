@@ -19,7 +19,7 @@ SS_TITLE, SS_BODY = 0, 1
 SS_FLAG_TIMING = 1
 
 EXPORTS = [
-    "ss_version", "ss_create", "ss_destroy", "ss_last_error", "ss_comm_unique_id", "ss_comm_init",
+    "ss_version", "ss_create", "ss_destroy", "ss_last_error", "ss_stream_handle", "ss_comm_unique_id", "ss_comm_init",
     "ss_graph_load_csr", "ss_pagerank", "ss_pagerank_fetch", "ss_pagerank_get_stats", "ss_index_load",
     "ss_index_clear",
     "ss_term_weights", "ss_set_doc_norms", "ss_set_pagerank", "ss_use_pagerank", "ss_score_batch",
@@ -38,7 +38,7 @@ class Config(C.Structure):
 
 
 class PagerankStats(C.Structure):
-    _fields_ = [("n_nodes", C.c_uint64), ("n_edges", C.c_uint64), ("local_rows", C.c_uint64),
+    _fields_ = [("n_nodes", C.c_uint64), ("n_edges", C.c_uint64), ("row_lo", C.c_uint64), ("local_rows", C.c_uint64),
                 ("local_edges", C.c_uint64), ("sweeps", C.c_uint32), ("launches", C.c_uint32),
                 ("sweep_ms_total", C.c_double), ("gather_ms_total", C.c_double),
                 ("exchange_ms_total", C.c_double), ("load_ms", C.c_double)]
@@ -74,6 +74,8 @@ def load():
     L.ss_destroy.argtypes = [vp]
     L.ss_destroy.restype = None
     L.ss_last_error.restype = C.c_char_p
+    L.ss_stream_handle.argtypes = [vp]
+    L.ss_stream_handle.restype = vp
     L.ss_comm_unique_id.argtypes = [vp]
     L.ss_comm_init.argtypes = [vp, vp, i32, i32]
     L.ss_graph_load_csr.argtypes = [vp, u64, u64, vp, vp]
@@ -90,7 +92,7 @@ def load():
     L.ss_merge_topk.argtypes = [vp, u32, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ss_score_get_stats.argtypes = [vp, C.POINTER(ScoreStats)]
     for name in EXPORTS:
-        if name not in ("ss_destroy", "ss_last_error"):
+        if name not in ("ss_destroy", "ss_last_error", "ss_stream_handle"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -155,6 +157,9 @@ class Engine:
 
     def __exit__(self, *exc):
         self.close()
+
+    def stream_handle(self) -> int:
+        return int(self.L.ss_stream_handle(self.h) or 0)
 
     # ---- multi-GPU
     def comm_init(self, unique_id: bytes, rank: int, world: int):

@@ -165,6 +165,8 @@ SS_API void ss_destroy(ss_engine* e) {
   delete e;
 }
 
+SS_API void* ss_stream_handle(ss_engine* e) { return e ? (void*)e->stream : nullptr; }
+
 SS_API int ss_comm_unique_id(void* id128) {
   SS_REQUIRE(id128, SS_ERR_INVALID, "ss_comm_unique_id: NULL");
   auto* api = ss::nccl_api();

@@ -38,6 +38,25 @@ struct IndexState {
   std::vector<double> sqd_probs;
   bool sqd_valid = false;
   ss_score_stats stats{};
+  // grow-only device workspace of ss_score_batch (cudaMalloc/cudaFree per batch would
+  // synchronise the device and dominate small batches)
+  struct Workspace {
+    ss::DevBuf<uint64_t> kw_ptr, ph_ptr;
+    ss::DevBuf<uint32_t> kw, ph, part_doc, part_count, out_doc, out_count;
+    ss::DevBuf<double> probs, part_final, part_pr, out_final, out_pr, zero_mag;
+    ss::DevBuf<unsigned long long> stats;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    ~Workspace() {
+      for (auto& e : ev)
+        if (e) cudaEventDestroy(e);
+    }
+  } ws;
 };
+
+template <class T>
+inline int ws_reserve(ss::DevBuf<T>& b, size_t n) {
+  if (b.p && b.n >= n) return SS_OK;
+  return b.alloc(n + n / 4);
+}
 
 IndexState* index_state(ss_engine* e);  // creates on first use; nullptr on OOM

@@ -723,6 +723,7 @@ SS_API int ss_graph_load_csr(ss_engine* e, uint64_t n_nodes, uint64_t n_edges, c
   for (auto& ev : s->ev) SS_CUDA(cudaEventCreate(&ev));
   s->stats.n_nodes = N;
   s->stats.n_edges = E;
+  s->stats.row_lo = s->row_lo;
   s->stats.local_rows = s->rows_loc;
   s->stats.local_edges = s->E_loc;
   s->stats.load_ms =

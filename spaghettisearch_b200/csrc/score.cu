@@ -23,6 +23,7 @@
 // lists for the doc-sharded multi-GPU path.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "index.cuh"
@@ -36,6 +37,7 @@ constexpr int kMaxK = 128;
 constexpr int kMaxKw = 64;     // keyword tokens per query handled in-kernel
 constexpr int kMaxPh = 32;     // phrase tokens per query handled in-kernel
 constexpr int kMaxLists = 2 * (kMaxKw + kMaxPh);
+constexpr int kBounds = 4096;   // sub-range boundary table entries per pass
 constexpr uint32_t kNoDoc = 0xFFFFFFFFu;
 
 struct TableView {
@@ -86,41 +88,76 @@ __device__ __forceinline__ bool beats(uint64_t ka, uint32_t da, uint64_t kb, uin
   return ka > kb || (ka == kb && da < db);
 }
 
-// first index in [lo, hi) with docs[i] >= target, galloping from lo
-__device__ __forceinline__ uint64_t gallop_lower_bound(const uint32_t* __restrict__ docs, uint64_t lo, uint64_t hi,
-                                                       uint64_t target) {
-  if (lo >= hi || docs[lo] >= target) return lo;
-  uint64_t step = 1, a = lo;  // docs[a] < target
-  while (a + step < hi && docs[a + step] < target) {
-    a += step;
-    step <<= 1;
+// first index in [lo, hi) with docs[i] >= target
+__device__ __forceinline__ uint64_t lower_bound_doc(const uint32_t* __restrict__ docs, uint64_t lo, uint64_t hi,
+                                                    uint64_t target) {
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (docs[mid] < target) lo = mid + 1; else hi = mid;
   }
-  uint64_t b = min(hi, a + step);  // answer in (a, b]
-  ++a;
-  while (a < b) {
-    const uint64_t mid = (a + b) >> 1;
-    if (docs[mid] < target) a = mid + 1; else b = mid;
-  }
-  return a;
+  return lo;
 }
 
 struct Smem {
   double acc[2][kRange];        // [0] TitleRank, [1] BodyRank sums of the sub-range
   unsigned long long cand_key[kCand];
   unsigned long long top_key[2][kMaxK];
-  unsigned long long cur[kMaxLists], end[kMaxLists], hi[kMaxLists];
+  unsigned long long cur[kMaxLists], hi[kMaxLists];  // current sub-range of every list
+  unsigned long long base[kMaxLists];               // start of the list inside the slab
+  uint32_t len[kMaxLists];                          // postings of the list inside the slab
+  uint32_t bounds[kBounds];                         // [list][sub-range] offsets from base
   uint32_t cand_doc[kCand];
   uint32_t top_doc[2][kMaxK];
   uint32_t bits[kRange / 32];
   uint32_t n_cand, top_n, top_buf;
-  unsigned long long thr_key;
-  uint32_t thr_doc;
+  unsigned long long thr_key, piv_key;
+  uint32_t thr_doc, piv_doc;
 };
 
 // Union of the running top-k and the candidate buffer -> new running top-k by
 // counting, for each element, how many others beat it (elements are distinct
-// in (key, doc), so ranks are a permutation).
+// in (key, doc), so ranks are a permutation).  A large candidate set is first
+// thinned with a pivot: the k-th best of a kSample-element sample is beaten by
+// at most k-1 sample members, so every candidate the pivot beats is outside
+// the top k and can be dropped without changing the result.
+constexpr uint32_t kSample = 128;
 __device__ void merge_candidates(Smem& s, uint32_t k) {
+  if (s.n_cand > 2 * kSample && 4 * k <= kSample) {
+    const uint32_t nc0 = s.n_cand;
+    if (threadIdx.x < kSample) {
+      const unsigned long long ki = s.cand_key[threadIdx.x];
+      const uint32_t di = s.cand_doc[threadIdx.x];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < kSample; ++j) rank += beats(s.cand_key[j], s.cand_doc[j], ki, di) ? 1u : 0u;
+      if (rank == k - 1) {
+        s.piv_key = ki;
+        s.piv_doc = di;
+      }
+    }
+    // survivors are re-packed: read into registers, barrier, write
+    constexpr int kPerThread = kCand / kT;
+    unsigned long long rk[kPerThread];
+    uint32_t rd[kPerThread];
+#pragma unroll
+    for (int c = 0; c < kPerThread; ++c) {
+      const uint32_t i = threadIdx.x + c * kT;
+      rk[c] = i < nc0 ? s.cand_key[i] : 0ull;
+      rd[c] = i < nc0 ? s.cand_doc[i] : kNoDoc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s.n_cand = 0;
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < kPerThread; ++c) {
+      const uint32_t i = threadIdx.x + c * kT;
+      if (i < nc0 && !beats(s.piv_key, s.piv_doc, rk[c], rd[c])) {
+        const uint32_t j = atomicAdd(&s.n_cand, 1u);
+        s.cand_key[j] = rk[c];
+        s.cand_doc[j] = rd[c];
+      }
+    }
+    __syncthreads();
+  }
   const uint32_t nt = s.top_n, nc = s.n_cand, n = nt + nc;
   const uint32_t ob = s.top_buf, nb = ob ^ 1;
   for (uint32_t i = threadIdx.x; i < n; i += kT) {
@@ -249,19 +286,36 @@ __global__ void __launch_bounds__(kT) k_score(ScoreParams p) {
       a = tv.term_ptr[term];
       b = tv.term_ptr[term + 1];
     }
-    a = gallop_lower_bound(tv.doc_ids, a, b, slab_lo);
-    s.cur[l] = a;
-    s.end[l] = gallop_lower_bound(tv.doc_ids, a, b, slab_hi);
+    a = lower_bound_doc(tv.doc_ids, a, b, slab_lo);
+    s.base[l] = a;
+    s.len[l] = (uint32_t)(lower_bound_doc(tv.doc_ids, a, b, slab_hi) - a);
   }
   __syncthreads();
 
   const double qm = sqrt((double)q_len);  // get_metadata.go:53
   unsigned long long n_postings = 0, n_matched = 0;
 
-  for (uint64_t d0 = slab_lo; d0 < slab_hi; d0 += kRange) {
+  // Sub-range boundaries of every list are found up front, all threads searching
+  // in parallel (one dependent-load chain per CTA pass instead of one per sub-range).
+  const uint32_t n_sub = (uint32_t)((slab_hi - slab_lo + kRange - 1) / kRange);
+  const uint32_t pass_sub = n_lists ? max(1u, min(n_sub, (uint32_t)kBounds / n_lists - 1u)) : n_sub;
+  for (uint32_t sub0 = 0; sub0 < n_sub; sub0 += pass_sub) {
+  const uint32_t nb = min(pass_sub, n_sub - sub0);
+  __syncthreads();
+  for (uint32_t idx = tid; idx < n_lists * (nb + 1); idx += kT) {
+    const uint32_t l = idx / (nb + 1), j = idx % (nb + 1);
+    const uint64_t target = min(slab_hi, slab_lo + (uint64_t)(sub0 + j) * kRange);
+    const uint32_t* docs = p.tab[l & 1].doc_ids;
+    s.bounds[idx] = s.len[l] ? (uint32_t)(lower_bound_doc(docs, s.base[l], s.base[l] + s.len[l], target) - s.base[l]) : 0u;
+  }
+  __syncthreads();
+  for (uint32_t sj = 0; sj < nb; ++sj) {
+    const uint64_t d0 = slab_lo + (uint64_t)(sub0 + sj) * kRange;
     const uint64_t d1 = min(slab_hi, d0 + kRange);
-    for (uint32_t l = tid; l < n_lists; l += kT)
-      s.hi[l] = gallop_lower_bound(p.tab[l & 1].doc_ids, s.cur[l], s.end[l], d1);
+    for (uint32_t l = tid; l < n_lists; l += kT) {
+      s.cur[l] = s.base[l] + s.bounds[l * (nb + 1) + sj];
+      s.hi[l] = s.base[l] + s.bounds[l * (nb + 1) + sj + 1];
+    }
     __syncthreads();
 
     // keyword tokens in query order (duplicates count again)
@@ -296,20 +350,31 @@ __global__ void __launch_bounds__(kT) k_score(ScoreParams p) {
     }
 
     if (any) {
-      const uint32_t n_slots = (uint32_t)(d1 - d0);
-      for (uint32_t c0 = 0; c0 < n_slots; c0 += kCand) {
-        for (uint32_t i = tid; i < kCand; i += kT) {
-          const uint32_t slot = c0 + i;
-          if (slot >= n_slots || !((s.bits[slot >> 5] >> (slot & 31)) & 1u)) continue;
+      // finish the matched docs, word by word of the bitmap (work follows the matches)
+      const uint32_t lane = tid & 31, warp = tid >> 5;
+      for (uint32_t w0 = 0; w0 < kRange / 32; w0 += kCand / 32) {
+        for (uint32_t wi = w0 + warp; wi < w0 + kCand / 32; wi += kT / 32) {
+          const uint32_t word = s.bits[wi];
+          if (!word) continue;  // warp uniform
+          __syncwarp();
+          if (lane == 0) s.bits[wi] = 0;
+          if (!((word >> lane) & 1u)) continue;
+          const uint32_t slot = wi * 32 + lane;
           const uint64_t doc = d0 + slot;
           const double tr = s.acc[0][slot], br = s.acc[1][slot];
           s.acc[0][slot] = 0.0;
           s.acc[1][slot] = 0.0;
           ++n_matched;
-          double body = __ddiv_rn(br, __dmul_rn(p.mag[1][doc], qm));   // get_metadata.go:57
-          double title = __ddiv_rn(tr, __dmul_rn(p.mag[0][doc], qm));  // :58
-          if (isnan(body)) body = 0.0;                                 // :61-66
-          if (isnan(title)) title = 0.0;
+          // get_metadata.go:57-66.  x/y with x == 0 is 0 or NaN, and NaN becomes 0: skip the divide
+          double body = 0.0, title = 0.0;
+          if (br != 0.0) {
+            body = __ddiv_rn(br, __dmul_rn(p.mag[1][doc], qm));
+            if (isnan(body)) body = 0.0;
+          }
+          if (tr != 0.0) {
+            title = __ddiv_rn(tr, __dmul_rn(p.mag[0][doc], qm));
+            if (isnan(title)) title = 0.0;
+          }
           double sqd = 0.0;  // :39-42
           if (p.sqd) {
             sqd = p.sqd[doc];
@@ -331,10 +396,9 @@ __global__ void __launch_bounds__(kT) k_score(ScoreParams p) {
         __syncthreads();
         if (s.n_cand) merge_candidates(s, k);
       }
-      for (uint32_t i = tid; i < kRange / 32; i += kT) s.bits[i] = 0;
     }
-    for (uint32_t l = tid; l < n_lists; l += kT) s.cur[l] = s.hi[l];
     __syncthreads();
+  }
   }
 
   // this slab's list
@@ -484,67 +548,15 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   cudaStream_t st = e->stream;
   const bool timing = (e->flags & SS_FLAG_TIMING) != 0;
   uint32_t launches = 0;
-
-  // a table that was never loaded behaves as an empty one with zero norms
-  ss::DevBuf<double> zero_mag;
-  for (int tb = 0; tb < 2; ++tb)
-    if (!ix->tab[tb].loaded && zero_mag.n == 0) {
-      SS_TRY(zero_mag.alloc(D));
-      SS_CUDA(cudaMemsetAsync(zero_mag.p, 0, std::max<uint64_t>(D, 1) * 8, st));
-    }
-
-  ss::DevBuf<uint64_t> d_kw_ptr, d_ph_ptr;
-  ss::DevBuf<uint32_t> d_kw, d_ph;
-  ss::DevBuf<double> d_probs;
-  SS_TRY(d_kw_ptr.alloc(n_q + 1));
-  SS_TRY(d_kw.alloc(n_kw));
-  SS_CUDA(cudaMemcpyAsync(d_kw_ptr.p, kw_ptr, (n_q + 1) * 8, cudaMemcpyHostToDevice, st));
-  if (n_kw) SS_CUDA(cudaMemcpyAsync(d_kw.p, kw_terms, n_kw * 4, cudaMemcpyHostToDevice, st));
-  if (ph_ptr) {
-    SS_TRY(d_ph_ptr.alloc(n_q + 1));
-    SS_TRY(d_ph.alloc(n_ph));
-    SS_CUDA(cudaMemcpyAsync(d_ph_ptr.p, ph_ptr, (n_q + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (n_ph) SS_CUDA(cudaMemcpyAsync(d_ph.p, ph_terms, n_ph * 4, cudaMemcpyHostToDevice, st));
-  }
-
-  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-  if (timing)
-    for (auto& x : ev) SS_CUDA(cudaEventCreate(&x));
-  struct EvGuard {
-    cudaEvent_t* ev;
-    ~EvGuard() {
-      for (int i = 0; i < 3; ++i)
-        if (ev[i]) cudaEventDestroy(ev[i]);
-    }
-  } ev_guard{ev};
-  if (timing) SS_CUDA(cudaEventRecord(ev[0], st));
-
-  // blend term: one pass over forw[3] for a shared topic vector, cached across batches
-  const double* sqd_ptr = nullptr;
-  if (blend && !probs_per_query) {
-    std::vector<double> h(topic_probs, topic_probs + ix->T);
-    const bool same = ix->sqd_valid && ix->sqd_probs.size() == h.size() &&
-                      memcmp(ix->sqd_probs.data(), h.data(), h.size() * 8) == 0;
-    if (!same) {
-      SS_TRY(d_probs.alloc(ix->T));
-      SS_CUDA(cudaMemcpyAsync(d_probs.p, topic_probs, ix->T * 8, cudaMemcpyHostToDevice, st));
-      if (ix->sqd.n != std::max<uint64_t>(D, 1)) SS_TRY(ix->sqd.alloc(D));
-      if (D) k_sqd<<<ss::div_up(D, 256), 256, 0, st>>>(ix->pr.p, d_probs.p, ix->T, D, ix->sqd.p);
-      ++launches;
-      ix->sqd_probs = h;
-      ix->sqd_valid = true;
-    }
-    sqd_ptr = ix->sqd.p;
-  } else if (blend) {
-    SS_TRY(d_probs.alloc(n_q * ix->T));
-    SS_CUDA(cudaMemcpyAsync(d_probs.p, topic_probs, n_q * ix->T * 8, cudaMemcpyHostToDevice, st));
-  }
+  IndexState::Workspace& ws = ix->ws;
 
   // slabs: enough CTAs to fill the machine, index slice per slab around the L2 size,
   // and n_slabs * k small enough for the merge kernel
   const uint64_t n_sub = std::max<uint64_t>(1, (D + kRange - 1) / kRange);
   const uint64_t index_bytes = (ix->tab[0].P + ix->tab[1].P) * 8;
-  uint64_t n_slabs = std::max<uint64_t>(1, (index_bytes + (64ull << 20) - 1) / (64ull << 20));
+  uint64_t slab_bytes = 64ull << 20;
+  if (const char* env = getenv("SS_SCORE_SLAB_MB")) slab_bytes = std::max(1ull, strtoull(env, nullptr, 10)) << 20;
+  uint64_t n_slabs = std::max<uint64_t>(1, (index_bytes + slab_bytes - 1) / slab_bytes);
   const uint64_t want_ctas = (uint64_t)e->sm_count * 16;
   n_slabs = std::max(n_slabs, (want_ctas + n_q - 1) / n_q);
   n_slabs = std::min<uint64_t>(n_slabs, n_sub);
@@ -553,71 +565,105 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   n_slabs = (n_sub + sub_per_slab - 1) / sub_per_slab;
   SS_REQUIRE(n_q * n_slabs < 0x7FFFFFFFull, SS_ERR_INVALID, "ss_score_batch: batch too large; split it");
 
-  ss::DevBuf<uint32_t> part_doc, part_count, d_out_doc, d_out_count;
-  ss::DevBuf<double> part_final, part_pr, d_out_final, d_out_pr;
-  ss::DevBuf<unsigned long long> d_stats;
-  SS_TRY(part_doc.alloc(n_q * n_slabs * k));
-  SS_TRY(part_final.alloc(n_q * n_slabs * k));
-  SS_TRY(part_pr.alloc(n_q * n_slabs * k));
-  SS_TRY(part_count.alloc(n_q * n_slabs));
-  SS_TRY(d_out_doc.alloc(n_q * k));
-  SS_TRY(d_out_final.alloc(n_q * k));
-  SS_TRY(d_out_pr.alloc(n_q * k));
-  SS_TRY(d_out_count.alloc(n_q));
-  SS_TRY(d_stats.alloc(2));
-  SS_CUDA(cudaMemsetAsync(d_stats.p, 0, 16, st));
+  // workspace (grow-only) and events: everything allocated before the timed region
+  SS_TRY(ws_reserve(ws.kw_ptr, n_q + 1));
+  SS_TRY(ws_reserve(ws.kw, n_kw));
+  if (ph_ptr) {
+    SS_TRY(ws_reserve(ws.ph_ptr, n_q + 1));
+    SS_TRY(ws_reserve(ws.ph, n_ph));
+  }
+  if (blend) SS_TRY(ws_reserve(ws.probs, probs_per_query ? n_q * ix->T : ix->T));
+  SS_TRY(ws_reserve(ws.part_doc, n_q * n_slabs * k));
+  SS_TRY(ws_reserve(ws.part_final, n_q * n_slabs * k));
+  SS_TRY(ws_reserve(ws.part_pr, n_q * n_slabs * k));
+  SS_TRY(ws_reserve(ws.part_count, n_q * n_slabs));
+  SS_TRY(ws_reserve(ws.out_doc, n_q * k));
+  SS_TRY(ws_reserve(ws.out_final, n_q * k));
+  SS_TRY(ws_reserve(ws.out_pr, n_q * k));
+  SS_TRY(ws_reserve(ws.out_count, n_q));
+  SS_TRY(ws_reserve(ws.stats, 2));
+  // a table that was never loaded behaves as an empty one with zero norms
+  if ((!ix->tab[0].loaded || !ix->tab[1].loaded) && ws.zero_mag.n < std::max<uint64_t>(D, 1)) {
+    SS_TRY(ws.zero_mag.alloc(D));
+    SS_CUDA(cudaMemsetAsync(ws.zero_mag.p, 0, std::max<uint64_t>(D, 1) * 8, st));
+  }
+  const bool shared_blend = blend && !probs_per_query;
+  bool sqd_fresh = false;
+  if (shared_blend) {
+    sqd_fresh = ix->sqd_valid && ix->sqd_probs.size() == ix->T &&
+                memcmp(ix->sqd_probs.data(), topic_probs, ix->T * 8) == 0;
+    if (!sqd_fresh && ix->sqd.n < std::max<uint64_t>(D, 1)) SS_TRY(ix->sqd.alloc(D));
+  }
+  if (timing)
+    for (auto& x : ws.ev)
+      if (!x) SS_CUDA(cudaEventCreate(&x));
+  SS_CUDA(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  SS_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeMax * 12));
+
+  if (timing) SS_CUDA(cudaEventRecord(ws.ev[0], st));
+  SS_CUDA(cudaMemcpyAsync(ws.kw_ptr.p, kw_ptr, (n_q + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (n_kw) SS_CUDA(cudaMemcpyAsync(ws.kw.p, kw_terms, n_kw * 4, cudaMemcpyHostToDevice, st));
+  if (ph_ptr) {
+    SS_CUDA(cudaMemcpyAsync(ws.ph_ptr.p, ph_ptr, (n_q + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_ph) SS_CUDA(cudaMemcpyAsync(ws.ph.p, ph_terms, n_ph * 4, cudaMemcpyHostToDevice, st));
+  }
+  SS_CUDA(cudaMemsetAsync(ws.stats.p, 0, 16, st));
+  // blend term: one pass over forw[3] for a shared topic vector, cached across batches
+  const double* sqd_ptr = nullptr;
+  if (shared_blend) {
+    if (!sqd_fresh) {
+      SS_CUDA(cudaMemcpyAsync(ws.probs.p, topic_probs, ix->T * 8, cudaMemcpyHostToDevice, st));
+      if (D) k_sqd<<<ss::div_up(D, 256), 256, 0, st>>>(ix->pr.p, ws.probs.p, ix->T, D, ix->sqd.p);
+      ++launches;
+      ix->sqd_probs.assign(topic_probs, topic_probs + ix->T);
+      ix->sqd_valid = true;
+    }
+    sqd_ptr = ix->sqd.p;
+  } else if (blend) {
+    SS_CUDA(cudaMemcpyAsync(ws.probs.p, topic_probs, n_q * ix->T * 8, cudaMemcpyHostToDevice, st));
+  }
 
   ScoreParams p{};
   p.tab[0] = view_of(ix->tab[0]);
   p.tab[1] = view_of(ix->tab[1]);
-  p.mag[0] = ix->tab[0].loaded ? ix->tab[0].mag.p : zero_mag.p;
-  p.mag[1] = ix->tab[1].loaded ? ix->tab[1].mag.p : zero_mag.p;
+  p.mag[0] = ix->tab[0].loaded ? ix->tab[0].mag.p : ws.zero_mag.p;
+  p.mag[1] = ix->tab[1].loaded ? ix->tab[1].mag.p : ws.zero_mag.p;
   p.sqd = sqd_ptr;
   p.pr = (blend && probs_per_query) ? ix->pr.p : nullptr;
-  p.probs = (blend && probs_per_query) ? d_probs.p : nullptr;
+  p.probs = (blend && probs_per_query) ? ws.probs.p : nullptr;
   p.T = ix->T;
   p.D = D;
-  p.kw_ptr = d_kw_ptr.p;
-  p.kw_terms = d_kw.p;
-  p.ph_ptr = ph_ptr ? d_ph_ptr.p : nullptr;
-  p.ph_terms = d_ph.p;
+  p.kw_ptr = ws.kw_ptr.p;
+  p.kw_terms = ws.kw.p;
+  p.ph_ptr = ph_ptr ? ws.ph_ptr.p : nullptr;
+  p.ph_terms = ws.ph.p;
   p.n_q = (uint32_t)n_q;
   p.n_slabs = (uint32_t)n_slabs;
   p.k = k;
   p.slab_docs = sub_per_slab * kRange;
-  p.part_doc = part_doc.p;
-  p.part_final = part_final.p;
-  p.part_pr = part_pr.p;
-  p.part_count = part_count.p;
-  p.stats = d_stats.p;
+  p.part_doc = ws.part_doc.p;
+  p.part_final = ws.part_final.p;
+  p.part_pr = ws.part_pr.p;
+  p.part_count = ws.part_count.p;
+  p.stats = ws.stats.p;
 
-  SS_CUDA(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  SS_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeMax * 12));
-  if (timing) SS_CUDA(cudaEventRecord(ev[1], st));
+  if (timing) SS_CUDA(cudaEventRecord(ws.ev[1], st));
   k_score<<<(unsigned)(n_q * n_slabs), kT, sizeof(Smem), st>>>(p);
-  if (timing) SS_CUDA(cudaEventRecord(ev[2], st));
-  k_merge<<<(unsigned)n_q, kT, (size_t)n_slabs * k * 12, st>>>((uint32_t)n_slabs, k, (uint32_t)n_q, 0, part_doc.p,
-                                                              part_final.p, part_pr.p, part_count.p, d_out_doc.p,
-                                                              d_out_final.p, d_out_pr.p, d_out_count.p);
+  if (timing) SS_CUDA(cudaEventRecord(ws.ev[2], st));
+  k_merge<<<(unsigned)n_q, kT, (size_t)n_slabs * k * 12, st>>>((uint32_t)n_slabs, k, (uint32_t)n_q, 0, ws.part_doc.p,
+                                                              ws.part_final.p, ws.part_pr.p, ws.part_count.p,
+                                                              ws.out_doc.p, ws.out_final.p, ws.out_pr.p,
+                                                              ws.out_count.p);
   launches += 2;
-  cudaEvent_t ev_end = nullptr;
-  if (timing) {
-    SS_CUDA(cudaEventCreate(&ev_end));
-    SS_CUDA(cudaEventRecord(ev_end, st));
-  }
-  SS_CUDA(cudaMemcpyAsync(out_doc, d_out_doc.p, n_q * k * 4, cudaMemcpyDeviceToHost, st));
-  SS_CUDA(cudaMemcpyAsync(out_final, d_out_final.p, n_q * k * 8, cudaMemcpyDeviceToHost, st));
-  SS_CUDA(cudaMemcpyAsync(out_pr, d_out_pr.p, n_q * k * 8, cudaMemcpyDeviceToHost, st));
-  SS_CUDA(cudaMemcpyAsync(out_count, d_out_count.p, n_q * 4, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(out_doc, ws.out_doc.p, n_q * k * 4, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(out_final, ws.out_final.p, n_q * k * 8, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(out_pr, ws.out_pr.p, n_q * k * 8, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(out_count, ws.out_count.p, n_q * 4, cudaMemcpyDeviceToHost, st));
   unsigned long long h_stats[2] = {0, 0};
-  SS_CUDA(cudaMemcpyAsync(h_stats, d_stats.p, 16, cudaMemcpyDeviceToHost, st));
-  cudaError_t sync_err = cudaStreamSynchronize(st);
-  if (sync_err == cudaSuccess) sync_err = cudaGetLastError();
-  if (sync_err != cudaSuccess) {
-    if (ev_end) cudaEventDestroy(ev_end);
-    ss::set_error("ss_score_batch: %s", cudaGetErrorString(sync_err));
-    return SS_ERR_CUDA;
-  }
+  SS_CUDA(cudaMemcpyAsync(h_stats, ws.stats.p, 16, cudaMemcpyDeviceToHost, st));
+  if (timing) SS_CUDA(cudaEventRecord(ws.ev[3], st));
+  SS_CUDA(cudaStreamSynchronize(st));
+  SS_CUDA(cudaGetLastError());
   ix->stats.postings_scanned = h_stats[0];
   ix->stats.docs_matched = h_stats[1];
   // SURVEY.md §8(d) B_q summed: 8 B per posting, per matched doc two norms + the blend
@@ -627,12 +673,11 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   ix->stats.launches = launches;
   if (timing) {
     float ms = 0;
-    cudaEventElapsedTime(&ms, ev[0], ev_end);
+    cudaEventElapsedTime(&ms, ws.ev[0], ws.ev[3]);  // H2D of the queries .. D2H of the results
     ix->stats.kernel_ms = ms;
-    cudaEventElapsedTime(&ms, ev[1], ev[2]);
+    cudaEventElapsedTime(&ms, ws.ev[1], ws.ev[2]);
     ix->stats.score_kernel_ms = ms;
   }
-  if (ev_end) cudaEventDestroy(ev_end);
   return SS_OK;
 }
 

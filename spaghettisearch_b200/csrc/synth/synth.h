@@ -31,6 +31,13 @@ int ss_synth_graph(uint64_t n_nodes, uint64_t target_edges, uint64_t seed,
                    int n_threads, uint64_t* row_ptr, uint32_t** col_idx_out,
                    uint64_t* n_edges_out);
 
+// Rows [u_lo, u_hi) of the same graph (row_ptr is [u_hi-u_lo+1], offsets local
+// to the slice); slices of one (n_nodes, target_edges, seed) concatenate to the
+// full graph, so ranks can generate disjoint slices independently.
+int ss_synth_graph_rows(uint64_t n_nodes, uint64_t target_edges, uint64_t seed, int n_threads,
+                        uint64_t u_lo, uint64_t u_hi, uint64_t* row_ptr, uint32_t** col_idx_out,
+                        uint64_t* n_edges_out);
+
 // numPages[t] = 50000 + 12345*t  (forw[5] "numPages", crawler/ODP-scraper.go:104-107)
 void ss_synth_topics(uint32_t n_topics, int64_t* num_pages);
 

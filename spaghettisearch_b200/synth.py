@@ -30,6 +30,10 @@ def lib():
         _lib.ss_synth_graph.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p,
                                         C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint64)]
         _lib.ss_synth_graph.restype = C.c_int
+        _lib.ss_synth_graph_rows.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64,
+                                             C.c_uint64, C.c_void_p, C.POINTER(C.POINTER(C.c_uint32)),
+                                             C.POINTER(C.c_uint64)]
+        _lib.ss_synth_graph_rows.restype = C.c_int
         _lib.ss_synth_topics.argtypes = [C.c_uint32, C.c_void_p]
         _lib.ss_synth_index_make.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_uint64,
                                              C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.POINTER(_CIndex)]
@@ -74,6 +78,24 @@ def graph(n_nodes: int, target_edges: int, seed: int = 42, n_threads: int = 0) -
     finally:
         L.ss_synth_free(col)
     return Graph(n_nodes, row_ptr, col_idx)
+
+
+def graph_rows(n_nodes: int, target_edges: int, u_lo: int, u_hi: int, seed: int = 42,
+               n_threads: int = 0) -> Graph:
+    """Rows [u_lo, u_hi) of graph(n_nodes, target_edges, seed); row_ptr is local to the slice."""
+    L = lib()
+    row_ptr = np.zeros(u_hi - u_lo + 1, dtype=np.uint64)
+    col = C.POINTER(C.c_uint32)()
+    ne = C.c_uint64(0)
+    rc = L.ss_synth_graph_rows(n_nodes, target_edges, seed, n_threads, u_lo, u_hi, row_ptr.ctypes.data,
+                               C.byref(col), C.byref(ne))
+    if rc != 0:
+        raise RuntimeError(f"ss_synth_graph_rows failed: {rc}")
+    try:
+        col_idx = _copy(col, ne.value, np.uint32)
+    finally:
+        L.ss_synth_free(col)
+    return Graph(u_hi - u_lo, row_ptr, col_idx)
 
 
 def topics(n_topics: int = 16) -> np.ndarray:

@@ -26,6 +26,16 @@ def test_graph_deterministic_and_thread_independent(built):
     assert not np.array_equal(a.col_idx[:1000], c.col_idx[:1000])
 
 
+def test_graph_row_slices_concatenate(built):
+    full = synth.graph(30000, 400000, seed=5)
+    parts = [synth.graph_rows(30000, 400000, lo, hi, seed=5, n_threads=2)
+             for lo, hi in ((0, 7000), (7000, 7001), (7001, 30000))]
+    assert sum(p.n_edges for p in parts) == full.n_edges
+    assert np.array_equal(np.concatenate([p.col_idx for p in parts]), full.col_idx)
+    assert np.array_equal(np.diff(full.row_ptr.astype(np.int64)),
+                          np.concatenate([np.diff(p.row_ptr.astype(np.int64)) for p in parts]))
+
+
 def test_graph_edge_cases(built):
     g = synth.graph(1, 10)
     assert g.n_nodes == 1 and g.n_edges <= 1
