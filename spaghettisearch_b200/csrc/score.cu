@@ -109,7 +109,7 @@ struct Smem {
   uint32_t cand_doc[kCand];
   uint32_t top_doc[2][kMaxK];
   uint32_t bits[kRange / 32];
-  uint32_t n_cand, top_n, top_buf;
+  uint32_t n_cand, n_ent, top_n, top_buf;
   unsigned long long thr_key, piv_key;
   uint32_t thr_doc, piv_doc;
 };
@@ -184,13 +184,22 @@ __device__ void merge_candidates(Smem& s, uint32_t k) {
   __syncthreads();
 }
 
-// phrase.go:53-109 for one table inside the current sub-range.  lists l0+2*i+tb
-// hold token i's narrowed posting range.  A doc gets ONE weight = fp32 sum of
-// the tokens' weights in phrase order iff every token has a posting in this
-// table and some position a of token 0 has a + i among token i's positions
-// (compared as (pos_i - float32(i)) == pos_0, phrase.go:144-146, util.go:185).
+// Sort-path entry: doc offset in the slab (24 bits) | list sequence (8) | weight bits (32).
+// Sorting the 64-bit keys groups a doc's weights in query-token order.
+constexpr uint32_t kSortMax = 2 * kRange;  // entries; the buffer aliases the two accumulator arrays
+__device__ __forceinline__ unsigned long long make_entry(uint32_t off, uint32_t seq, float w) {
+  return ((unsigned long long)off << 40) | ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(w);
+}
+
+// phrase.go:53-109 for one table over the lists' current ranges [cur, hi).  Lists
+// l0+2*i+tb hold token i.  A doc gets ONE weight = fp32 sum of the tokens' weights
+// in phrase order iff every token has a posting in this table and some position a
+// of token 0 has a + i among token i's positions (compared as
+// (pos_i - float32(i)) == pos_0, phrase.go:144-146, util.go:185).
+// EMIT = false: add into the sub-range accumulators; EMIT = true: append a sort entry.
+template <bool EMIT>
 __device__ void apply_phrase(const ScoreParams& p, Smem& s, int tb, uint32_t l0, uint32_t L, uint64_t d0,
-                             unsigned long long& n_postings) {
+                             uint32_t seq, unsigned long long& n_postings) {
   const TableView& tv = p.tab[tb];
   uint32_t drv = 0;
   unsigned long long best = ~0ull;
@@ -243,8 +252,163 @@ __device__ void apply_phrase(const ScoreParams& p, Smem& s, int tb, uint32_t l0,
     float sum = 0.0f;  // phrase.go:59,69,83: float32 running sum in token order
     for (uint32_t i = 0; i < L; ++i) sum = __fadd_rn(sum, tv.w[pi[i]]);
     const uint32_t slot = (uint32_t)(doc - d0);
-    s.acc[tb][slot] = __dadd_rn(s.acc[tb][slot], (double)sum);
-    atomicOr(&s.bits[slot >> 5], 1u << (slot & 31));
+    if (EMIT) {
+      unsigned long long* ent = reinterpret_cast<unsigned long long*>(&s.acc[0][0]);
+      ent[atomicAdd(&s.n_ent, 1u)] = make_entry(slot, seq, sum);
+    } else {
+      s.acc[tb][slot] = __dadd_rn(s.acc[tb][slot], (double)sum);
+      atomicOr(&s.bits[slot >> 5], 1u << (slot & 31));
+    }
+  }
+}
+
+// Per-doc inputs of the final rank, fetched together so that their latencies overlap.
+struct DocMeta {
+  double mag_t, mag_b, sqd;
+};
+__device__ __forceinline__ DocMeta load_meta(const ScoreParams& p, uint32_t q, uint64_t doc) {
+  DocMeta m;
+  m.mag_b = p.mag[1][doc];
+  m.mag_t = p.mag[0][doc];
+  m.sqd = 0.0;  // get_metadata.go:39-42
+  if (p.sqd) {
+    m.sqd = p.sqd[doc];
+  } else if (p.probs) {
+    const double* pr = p.pr + doc * p.T;
+    const double* pq = p.probs + (uint64_t)q * p.T;
+    for (uint32_t t = 0; t < p.T; ++t) m.sqd = __dadd_rn(m.sqd, __dmul_rn(pq[t], pr[t]));
+  }
+  return m;
+}
+
+// cosine, NaN -> 0, PageRank blend (get_metadata.go:53-69); a doc that can still
+// make the top k goes to the candidate buffer.
+__device__ __forceinline__ void finish_doc(Smem& s, uint64_t doc, double tr, double br, const DocMeta& m, double qm,
+                                           uint32_t k) {
+  // get_metadata.go:57-66.  x/y with x == 0 is 0 or NaN, and NaN becomes 0: skip the divide
+  double body = 0.0, title = 0.0;
+  if (br != 0.0) {
+    body = __ddiv_rn(br, __dmul_rn(m.mag_b, qm));
+    if (isnan(body)) body = 0.0;
+  }
+  if (tr != 0.0) {
+    title = __ddiv_rn(tr, __dmul_rn(m.mag_t, qm));
+    if (isnan(title)) title = 0.0;
+  }
+  // (0.33*sqd + 0.38*Title + 0.29*Body) * 100.0, left to right, no fusing (:69)
+  const double fin =
+      __dmul_rn(__dadd_rn(__dadd_rn(__dmul_rn(0.33, m.sqd), __dmul_rn(0.38, title)), __dmul_rn(0.29, body)), 100.0);
+  const unsigned long long key = score_key(fin);
+  if (s.top_n < k || beats(key, (uint32_t)doc, s.thr_key, s.thr_doc)) {
+    const uint32_t j = atomicAdd(&s.n_cand, 1u);
+    s.cand_key[j] = key;
+    s.cand_doc[j] = (uint32_t)doc;
+  }
+}
+
+// One list's postings of the sub-range into the accumulators; a list holds a doc at
+// most once, so plain read-modify-write is race free.  Four postings per thread are
+// fetched before the first is applied.
+__device__ __forceinline__ void accumulate_list(const TableView& tv, Smem& s, int tb, unsigned long long x0,
+                                                unsigned long long x1, uint64_t d0) {
+  constexpr int U = 4;
+  for (unsigned long long x = x0 + threadIdx.x; x < x1; x += (unsigned long long)U * kT) {
+    uint32_t d[U];
+    float w[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long xx = x + (unsigned long long)u * kT;
+      const bool ok = xx < x1;
+      d[u] = ok ? tv.doc_ids[xx] : 0xFFFFFFFFu;
+      w[u] = ok ? tv.w[xx] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (d[u] == 0xFFFFFFFFu) continue;
+      const uint32_t slot = (uint32_t)(d[u] - d0);
+      s.acc[tb][slot] = __dadd_rn(s.acc[tb][slot], (double)w[u]);
+      atomicOr(&s.bits[slot >> 5], 1u << (slot & 31));
+    }
+  }
+}
+
+// Sparse (query, slab) pairs: all postings of the slab fit in shared memory.  They are
+// tagged (doc offset, list sequence, weight), sorted, and every doc's run is folded in
+// sequence order -- the same sums as the dense path without touching empty sub-ranges.
+__device__ void sort_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t slab_lo, uint32_t n_kw, uint32_t n_ph,
+                          double qm, uint32_t k, unsigned long long& n_postings, unsigned long long& n_matched) {
+  unsigned long long* ent = reinterpret_cast<unsigned long long*>(&s.acc[0][0]);
+  const uint32_t tid = threadIdx.x, n_kw_lists = 2 * n_kw;
+  if (tid == 0) {
+    uint32_t run = 0;
+    for (uint32_t l = 0; l < n_kw_lists; ++l) {
+      s.bounds[l] = run;
+      run += s.len[l];
+    }
+    s.bounds[n_kw_lists] = run;
+    s.n_ent = run;
+  }
+  for (uint32_t l = n_kw_lists + tid; l < n_kw_lists + 2 * n_ph; l += kT) {  // phrase lists: whole slab range
+    s.cur[l] = s.base[l];
+    s.hi[l] = s.base[l] + s.len[l];
+  }
+  __syncthreads();
+  const uint32_t total_kw = s.bounds[n_kw_lists];
+  for (uint32_t idx = tid; idx < total_kw; idx += kT) {
+    uint32_t lo = 0, hi = n_kw_lists;  // last l with bounds[l] <= idx
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (s.bounds[mid] <= idx) lo = mid; else hi = mid;
+    }
+    const TableView& tv = p.tab[lo & 1];
+    const unsigned long long at = s.base[lo] + (idx - s.bounds[lo]);
+    ent[idx] = make_entry((uint32_t)(tv.doc_ids[at] - slab_lo), lo, tv.w[at]);
+  }
+  if (tid == 0) n_postings += total_kw;
+  if (n_ph) {
+    apply_phrase<true>(p, s, 1, n_kw_lists, n_ph, slab_lo, n_kw_lists + 1, n_postings);
+    apply_phrase<true>(p, s, 0, n_kw_lists, n_ph, slab_lo, n_kw_lists, n_postings);
+  }
+  __syncthreads();
+  const uint32_t n = s.n_ent;
+  uint32_t n2 = 2;
+  while (n2 < n) n2 <<= 1;
+  for (uint32_t i = n + tid; i < n2; i += kT) ent[i] = ~0ull;
+  __syncthreads();
+  for (uint32_t kk = 2; kk <= n2; kk <<= 1) {
+    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = tid; i < n2; i += kT) {
+        const uint32_t x = i ^ j;
+        if (x > i) {
+          const unsigned long long a = ent[i], b = ent[x];
+          if ((a > b) == ((i & kk) == 0)) {
+            ent[i] = b;
+            ent[x] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (uint32_t r0 = 0; r0 < n; r0 += kCand) {
+    const uint32_t r1 = min(n, r0 + kCand);
+    for (uint32_t i = r0 + tid; i < r1; i += kT) {
+      const unsigned long long e0 = ent[i];
+      const uint32_t off = (uint32_t)(e0 >> 40);
+      if (i > 0 && (uint32_t)(ent[i - 1] >> 40) == off) continue;  // not the head of a doc's run
+      double tr = 0.0, br = 0.0;
+      for (uint32_t j = i; j < n; ++j) {
+        const unsigned long long e = ent[j];
+        if ((uint32_t)(e >> 40) != off) break;
+        const double w = (double)__uint_as_float((uint32_t)e);
+        if ((e >> 32) & 1ull) br = __dadd_rn(br, w); else tr = __dadd_rn(tr, w);
+      }
+      ++n_matched;
+      const DocMeta m = load_meta(p, q, slab_lo + off);
+      finish_doc(s, slab_lo + off, tr, br, m, qm, k);
+    }
+    __syncthreads();
+    if (s.n_cand) merge_candidates(s, k);
   }
 }
 
@@ -264,13 +428,9 @@ __global__ void __launch_bounds__(kT) k_score(ScoreParams p) {
   const uint64_t slab_hi = min(p.D, slab_lo + p.slab_docs);
   const uint32_t k = p.k;
 
-  for (uint32_t i = tid; i < kRange; i += kT) {
-    s.acc[0][i] = 0.0;
-    s.acc[1][i] = 0.0;
-  }
-  for (uint32_t i = tid; i < kRange / 32; i += kT) s.bits[i] = 0;
   if (tid == 0) {
     s.n_cand = 0;
+    s.n_ent = 0;
     s.top_n = 0;
     s.top_buf = 0;
     s.thr_key = 0;
@@ -292,9 +452,27 @@ __global__ void __launch_bounds__(kT) k_score(ScoreParams p) {
   }
   __syncthreads();
 
+  // how much work is there in this slab?  (uniform: every thread reads the same shared values)
+  unsigned long long work = 0;
+  for (uint32_t l = 0; l < 2 * n_kw; ++l) work += s.len[l];
+  for (int tb = 0; tb < 2 && n_ph; ++tb) {
+    uint32_t mn = 0xFFFFFFFFu;
+    for (uint32_t i = 0; i < n_ph; ++i) mn = min(mn, s.len[2 * n_kw + 2 * i + tb]);
+    work += mn;  // a phrase can hit at most once per posting of its shortest list
+  }
   const double qm = sqrt((double)q_len);  // get_metadata.go:53
   unsigned long long n_postings = 0, n_matched = 0;
 
+  if (work == 0) {
+    // nothing of this query lives in this slab
+  } else if (work <= kSortMax && p.slab_docs <= (1ull << 24)) {
+    sort_path(p, s, q, slab_lo, n_kw, n_ph, qm, k, n_postings, n_matched);
+  } else {
+  for (uint32_t i = tid; i < kRange; i += kT) {
+    s.acc[0][i] = 0.0;
+    s.acc[1][i] = 0.0;
+  }
+  for (uint32_t i = tid; i < kRange / 32; i += kT) s.bits[i] = 0;
   // Sub-range boundaries of every list are found up front, all threads searching
   // in parallel (one dependent-load chain per CTA pass instead of one per sub-range).
   const uint32_t n_sub = (uint32_t)((slab_hi - slab_lo + kRange - 1) / kRange);
@@ -311,7 +489,6 @@ __global__ void __launch_bounds__(kT) k_score(ScoreParams p) {
   __syncthreads();
   for (uint32_t sj = 0; sj < nb; ++sj) {
     const uint64_t d0 = slab_lo + (uint64_t)(sub0 + sj) * kRange;
-    const uint64_t d1 = min(slab_hi, d0 + kRange);
     for (uint32_t l = tid; l < n_lists; l += kT) {
       s.cur[l] = s.base[l] + s.bounds[l * (nb + 1) + sj];
       s.hi[l] = s.base[l] + s.bounds[l * (nb + 1) + sj + 1];
@@ -324,16 +501,8 @@ __global__ void __launch_bounds__(kT) k_score(ScoreParams p) {
       const unsigned long long t0 = s.cur[2 * i], t1 = s.hi[2 * i], b0 = s.cur[2 * i + 1], b1 = s.hi[2 * i + 1];
       if (t1 == t0 && b1 == b0) continue;
       any = true;
-      for (unsigned long long x = b0 + tid; x < b1; x += kT) {
-        const uint32_t slot = (uint32_t)(p.tab[1].doc_ids[x] - d0);
-        s.acc[1][slot] = __dadd_rn(s.acc[1][slot], (double)p.tab[1].w[x]);
-        atomicOr(&s.bits[slot >> 5], 1u << (slot & 31));
-      }
-      for (unsigned long long x = t0 + tid; x < t1; x += kT) {
-        const uint32_t slot = (uint32_t)(p.tab[0].doc_ids[x] - d0);
-        s.acc[0][slot] = __dadd_rn(s.acc[0][slot], (double)p.tab[0].w[x]);
-        atomicOr(&s.bits[slot >> 5], 1u << (slot & 31));
-      }
+      accumulate_list(p.tab[1], s, 1, b0, b1, d0);
+      accumulate_list(p.tab[0], s, 0, t0, t1, d0);
       if (tid == 0) n_postings += (t1 - t0) + (b1 - b0);
       __syncthreads();
     }
@@ -343,55 +512,41 @@ __global__ void __launch_bounds__(kT) k_score(ScoreParams p) {
       for (uint32_t i = 0; i < 2 * n_ph; ++i) ph_any |= s.hi[2 * n_kw + i] != s.cur[2 * n_kw + i];
       if (ph_any) {
         any = true;
-        apply_phrase(p, s, 1, 2 * n_kw, n_ph, d0, n_postings);
-        apply_phrase(p, s, 0, 2 * n_kw, n_ph, d0, n_postings);
+        apply_phrase<false>(p, s, 1, 2 * n_kw, n_ph, d0, 0, n_postings);
+        apply_phrase<false>(p, s, 0, 2 * n_kw, n_ph, d0, 0, n_postings);
         __syncthreads();
       }
     }
 
     if (any) {
-      // finish the matched docs, word by word of the bitmap (work follows the matches)
+      // finish the matched docs, word by word of the bitmap (work follows the matches);
+      // a lane's docs of one round are fetched together before any of them is scored
       const uint32_t lane = tid & 31, warp = tid >> 5;
+      constexpr int kWordsPerWarp = kCand / 32 / (kT / 32);
       for (uint32_t w0 = 0; w0 < kRange / 32; w0 += kCand / 32) {
-        for (uint32_t wi = w0 + warp; wi < w0 + kCand / 32; wi += kT / 32) {
+        bool has[kWordsPerWarp];
+        uint32_t slot[kWordsPerWarp];
+        DocMeta meta[kWordsPerWarp];
+        double tr[kWordsPerWarp], br[kWordsPerWarp];
+#pragma unroll
+        for (int r = 0; r < kWordsPerWarp; ++r) {
+          const uint32_t wi = w0 + warp + r * (kT / 32);
           const uint32_t word = s.bits[wi];
-          if (!word) continue;  // warp uniform
-          __syncwarp();
-          if (lane == 0) s.bits[wi] = 0;
-          if (!((word >> lane) & 1u)) continue;
-          const uint32_t slot = wi * 32 + lane;
-          const uint64_t doc = d0 + slot;
-          const double tr = s.acc[0][slot], br = s.acc[1][slot];
-          s.acc[0][slot] = 0.0;
-          s.acc[1][slot] = 0.0;
+          has[r] = (word >> lane) & 1u;
+          slot[r] = wi * 32 + lane;
+          meta[r] = load_meta(p, q, d0 + (has[r] ? slot[r] : 0u));
+          tr[r] = s.acc[0][slot[r]];
+          br[r] = s.acc[1][slot[r]];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < kWordsPerWarp; ++r) {
+          if (lane == 0) s.bits[w0 + warp + r * (kT / 32)] = 0;
+          if (!has[r]) continue;
+          s.acc[0][slot[r]] = 0.0;
+          s.acc[1][slot[r]] = 0.0;
           ++n_matched;
-          // get_metadata.go:57-66.  x/y with x == 0 is 0 or NaN, and NaN becomes 0: skip the divide
-          double body = 0.0, title = 0.0;
-          if (br != 0.0) {
-            body = __ddiv_rn(br, __dmul_rn(p.mag[1][doc], qm));
-            if (isnan(body)) body = 0.0;
-          }
-          if (tr != 0.0) {
-            title = __ddiv_rn(tr, __dmul_rn(p.mag[0][doc], qm));
-            if (isnan(title)) title = 0.0;
-          }
-          double sqd = 0.0;  // :39-42
-          if (p.sqd) {
-            sqd = p.sqd[doc];
-          } else if (p.probs) {
-            const double* pr = p.pr + doc * p.T;
-            const double* pq = p.probs + (uint64_t)q * p.T;
-            for (uint32_t t = 0; t < p.T; ++t) sqd = __dadd_rn(sqd, __dmul_rn(pq[t], pr[t]));
-          }
-          // (0.33*sqd + 0.38*Title + 0.29*Body) * 100.0, left to right, no fusing (:69)
-          const double fin = __dmul_rn(
-              __dadd_rn(__dadd_rn(__dmul_rn(0.33, sqd), __dmul_rn(0.38, title)), __dmul_rn(0.29, body)), 100.0);
-          const unsigned long long key = score_key(fin);
-          if (s.top_n < k || beats(key, (uint32_t)doc, s.thr_key, s.thr_doc)) {
-            const uint32_t j = atomicAdd(&s.n_cand, 1u);
-            s.cand_key[j] = key;
-            s.cand_doc[j] = (uint32_t)doc;
-          }
+          finish_doc(s, d0 + slot[r], tr[r], br[r], meta[r], qm, k);
         }
         __syncthreads();
         if (s.n_cand) merge_candidates(s, k);
@@ -400,8 +555,10 @@ __global__ void __launch_bounds__(kT) k_score(ScoreParams p) {
     __syncthreads();
   }
   }
+  }
 
   // this slab's list
+  __syncthreads();
   const size_t base = ((size_t)q * p.n_slabs + slab) * k;
   const uint32_t tb = s.top_buf, tn = s.top_n;
   for (uint32_t j = tid; j < k; j += kT) {
