@@ -135,7 +135,7 @@ def pin_view(t, dtype):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from spaghettisearch_b200 import capi, synth
+    from spaghettisearch_b200 import capi, sharding, synth
 
     rank, local, world = dist_env(args)
     torch.cuda.set_device(local)
@@ -166,9 +166,7 @@ def run_ours(args):
 
     eng = capi.Engine(device=local, timing=True)
     if world > 1:
-        obj = [capi.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(obj, src=0)
-        eng.comm_init(obj[0], rank, world)
+        eng.comm_init(sharding.share_unique_id(capi.comm_unique_id), rank, world)
     ext = torch.cuda.ExternalStream(eng.stream_handle(), device=torch.device("cuda", local))
     out = {}
 
@@ -181,22 +179,10 @@ def run_ours(args):
             row_ptr, col_idx = g.row_ptr, g.col_idx
         else:
             # each rank generates a slice of the rows, slices are exchanged over NCCL
-            lo, hi = n_nodes * rank // world, n_nodes * (rank + 1) // world
+            lo, hi = sharding.row_slice(rank, world, n_nodes)
             part = synth.graph_rows(n_nodes, n_edges_target, lo, hi, seed=42, n_threads=threads)
-            deg = torch.from_numpy(np.diff(part.row_ptr.astype(np.int64))).cuda()
-            cnt = torch.tensor([part.n_edges], dtype=torch.int64, device="cuda")
-            cnts = [torch.zeros_like(cnt) for _ in range(world)]
-            dist.all_gather(cnts, cnt)
-            cnts = [int(c.item()) for c in cnts]
-            degs = [torch.zeros(n_nodes * (r + 1) // world - n_nodes * r // world, dtype=torch.int64, device="cuda")
-                    for r in range(world)]
-            dist.all_gather(degs, deg)
-            cols = [torch.zeros(c, dtype=torch.int32, device="cuda") for c in cnts]
-            dist.all_gather(cols, torch.from_numpy(part.col_idx.view(np.int32)).cuda())
-            row_ptr = np.zeros(n_nodes + 1, dtype=np.uint64)
-            row_ptr[1:] = torch.cumsum(torch.cat(degs), 0).cpu().numpy().astype(np.uint64)
-            col_idx = torch.cat(cols).cpu().numpy().view(np.uint32)
-            del deg, degs, cols, part
+            row_ptr, col_idx = sharding.assemble_graph(n_nodes, part.row_ptr, part.col_idx, device="cuda")
+            del part
             torch.cuda.empty_cache()
         E = int(row_ptr[-1])
         gen_s = time.time() - t0
@@ -304,7 +290,8 @@ def run_scoring(args, eng, ext, rank, world, local, threads, cores, peak, peak_s
     import torch
     from spaghettisearch_b200 import capi, synth
     D, V, Q = args.docs * world, args.terms, args.queries
-    lo, hi = D * rank // world, D * (rank + 1) // world  # doc shard
+    from spaghettisearch_b200 import sharding
+    lo, hi = sharding.doc_shard(rank, world, D)
     t0 = time.time()
     title = synth.index_table(V, D, 0, doc_lo=lo, doc_hi=hi, n_threads=threads)
     body = synth.index_table(V, D, 1, doc_lo=lo, doc_hi=hi, n_threads=threads)
