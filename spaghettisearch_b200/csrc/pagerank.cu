@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "comm.cuh"
@@ -37,6 +38,9 @@
 
 namespace {
 
+#ifndef SS_GATHER_EVICT_LAST
+#define SS_GATHER_EVICT_LAST 0
+#endif
 constexpr uint32_t kShortMax = 32;   // longest row handled by one sub-warp
 constexpr uint32_t kChunk = 512;     // edges per long-row task
 constexpr int kThreads = 256;
@@ -59,7 +63,7 @@ struct SweepParams {
   const uint64_t* in_ptr;   // [rows_loc + 1], offsets into in_src
   const uint32_t* in_src;   // sources ascending within a row
   const double* mul;        // [rows_loc] d/out, or 0 for dangling rows
-  const double* tot;        // [TP] S_t + (1-d) N
+  const double* inv_tot;    // [TP] 1 / (S_t + (1-d) N)
   const double* init;       // [TP] 1/num_pages[t]
   double* red;              // [slots][3*TP] per-CTA partial sums (delta, S, changed)
   uint64_t row_lo;          // global id of local row 0
@@ -69,95 +73,147 @@ struct SweepParams {
   int first;                // sweep 1: add 1/n, compare against 1/n
 };
 
-__device__ __forceinline__ double2 ld_row_gather(const double* p) {
-  return __ldg(reinterpret_cast<const double2*>(p));
+// ---- row access -------------------------------------------------------------
+// A lane owns VEC consecutive topics of a row: VEC = 2 is a 128-bit access,
+// VEC = 4 the 256-bit LDG/STG that sm_100 adds (LDG.E.ENL2.256), which halves
+// the lanes per 128-byte row and doubles the rows a warp keeps in flight.
+template <int VEC>
+struct Vec {
+  double v[VEC];
+};
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> ld_row_gather(const double* p);
+template <>
+__device__ __forceinline__ Vec<2> ld_row_gather<2>(const double* p) {
+  const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+  return Vec<2>{{t.x, t.y}};
 }
-__device__ __forceinline__ double2 ld_row_stream(const double* p) {
-  return __ldcs(reinterpret_cast<const double2*>(p));
+template <>
+__device__ __forceinline__ Vec<4> ld_row_gather<4>(const double* p) {
+  Vec<4> r;
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+               : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3])
+               : "l"(p));
+  return r;
 }
-__device__ __forceinline__ void st_row_stream(double* p, double2 v) {
-  __stcs(reinterpret_cast<double2*>(p), v);
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> ld_row_stream(const double* p);
+template <>
+__device__ __forceinline__ Vec<2> ld_row_stream<2>(const double* p) {
+  const double2 t = __ldcs(reinterpret_cast<const double2*>(p));
+  return Vec<2>{{t.x, t.y}};
+}
+template <>
+__device__ __forceinline__ Vec<4> ld_row_stream<4>(const double* p) {
+  Vec<4> r;
+  asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];"
+               : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3])
+               : "l"(p));
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ void st_row_stream(double* p, const Vec<VEC>& v);
+template <>
+__device__ __forceinline__ void st_row_stream<2>(double* p, const Vec<2>& v) {
+  __stcs(reinterpret_cast<double2*>(p), make_double2(v.v[0], v.v[1]));
+}
+template <>
+__device__ __forceinline__ void st_row_stream<4>(double* p, const Vec<4>& v) {
+  asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v.v[0]), "d"(v.v[1]), "d"(v.v[2]),
+               "d"(v.v[3])
+               : "memory");
+}
+template <int VEC>
+__device__ __forceinline__ void st_row_plain(double* p, const Vec<VEC>& v) {
+#pragma unroll
+  for (int j = 0; j < VEC; j += 2) *reinterpret_cast<double2*>(p + j) = make_double2(v.v[j], v.v[j + 1]);
+}
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> ld_row_plain(const double* p) {
+  Vec<VEC> r;
+#pragma unroll
+  for (int j = 0; j < VEC; j += 2) {
+    const double2 t = *reinterpret_cast<const double2*>(p + j);
+    r.v[j] = t.x;
+    r.v[j + 1] = t.y;
+  }
+  return r;
 }
 
-struct Acc {  // per-thread running sums for its two topic columns
-  double d0 = 0, d1 = 0, s0 = 0, s1 = 0, c0 = 0, c1 = 0;
+template <int VEC>
+struct Acc {  // per-thread running sums for its VEC topic columns
+  double d[VEC], s[VEC], c[VEC];
+  __device__ Acc() {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) d[j] = s[j] = c[j] = 0.0;
+  }
 };
 
 // Fused normalise / teleport / residual for one finished row; executed by the
-// LPR lanes that own the row, lane l8 holding topics 2*l8 and 2*l8+1.  The
+// LPR lanes that own the row, lane l8 holding topics VEC*l8 .. VEC*l8+VEC-1.  The
 // row's own previous value yl and scale m are loaded by the caller (early, so
 // that they overlap the gathers).
-template <int LPR>
-__device__ __forceinline__ void epilogue(const SweepParams& p, uint32_t r, int l8, double a0, double a1,
-                                         double2 yl, double m, Acc& acc) {
-  constexpr int TP = 2 * LPR;
+template <int LPR, int VEC>
+__device__ __forceinline__ void epilogue(const SweepParams& p, uint32_t r, int l8, Vec<VEC> a, const Vec<VEC>& yl,
+                                         double m, Acc<VEC>& acc) {
+  constexpr int TP = LPR * VEC;
   const uint64_t v = p.row_lo + r;
   const bool has_out = m > 0.0;
   const double mul = has_out ? m : 1.0;
-  const double2 tot = *reinterpret_cast<const double2*>(p.tot + 2 * l8);
-  double2 yn;
-  {
-    const int t = 2 * l8;
-    double last_rank = yl.x / mul;
+  // One reciprocal per row instead of two fp64 divides per topic: the previous rank
+  // (only used for the residual) is y * (1/m), and the new rank multiplies by the
+  // per-topic 1/Tot computed once per sweep.  Both differ from the divide by <= 1 ulp,
+  // five orders of magnitude inside the 1e-9 L1 budget.
+  const double inv_mul = has_out ? 1.0 / m : 1.0;
+  const Vec<VEC> inv_tot = ld_row_plain<VEC>(p.inv_tot + VEC * l8);
+  Vec<VEC> yn;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int t = VEC * l8 + j;
+    double last_rank = yl.v[j] * inv_mul;
     if (p.first) {
       const double i0 = p.init[t];
-      a0 += i0;
+      a.v[j] += i0;
       last_rank = i0;
     }
     if ((p.active_mask >> t) & 1u) {
-      double nr = (a0 + p.tele) / tot.x;
-      acc.d0 += fabs(nr - last_rank);
-      yn.x = nr * mul;
-      acc.c0 += (__double_as_longlong(yn.x) != __double_as_longlong(yl.x)) ? 1.0 : 0.0;
+      const double nr = (a.v[j] + p.tele) * inv_tot.v[j];
+      acc.d[j] += fabs(nr - last_rank);
+      yn.v[j] = nr * mul;
+      acc.c[j] += (__double_as_longlong(yn.v[j]) != __double_as_longlong(yl.v[j])) ? 1.0 : 0.0;
     } else {
-      yn.x = yl.x;
+      yn.v[j] = yl.v[j];
     }
-    if (has_out) acc.s0 += yn.x;
+    if (has_out) acc.s[j] += yn.v[j];
   }
-  {
-    const int t = 2 * l8 + 1;
-    double last_rank = yl.y / mul;
-    if (p.first) {
-      const double i1 = p.init[t];
-      a1 += i1;
-      last_rank = i1;
-    }
-    if ((p.active_mask >> t) & 1u) {
-      double nr = (a1 + p.tele) / tot.y;
-      acc.d1 += fabs(nr - last_rank);
-      yn.y = nr * mul;
-      acc.c1 += (__double_as_longlong(yn.y) != __double_as_longlong(yl.y)) ? 1.0 : 0.0;
-    } else {
-      yn.y = yl.y;
-    }
-    if (has_out) acc.s1 += yn.y;
-  }
-  st_row_stream(p.y_next + v * TP + 2 * l8, yn);
+  st_row_stream<VEC>(p.y_next + v * TP + VEC * l8, yn);
 }
 
 // CTA-wide fixed-shape reduction of the per-thread sums into red[blockIdx.x].
-template <int LPR>
-__device__ __forceinline__ void block_reduce(const SweepParams& p, Acc acc, bool owner) {
-  constexpr int TP = 2 * LPR;
+template <int LPR, int VEC>
+__device__ __forceinline__ void block_reduce(const SweepParams& p, const Acc<VEC>& acc, bool owner) {
+  constexpr int TP = LPR * VEC;
   constexpr int kWarps = kThreads / 32;
   __shared__ double sm[kWarps][3 * 16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l8 = lane % LPR;
-  double v[6] = {acc.d0, acc.d1, acc.s0, acc.s1, acc.c0, acc.c1};
-  if (!owner) {
+  double v[3 * VEC];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) v[i] = 0.0;
+  for (int j = 0; j < VEC; ++j) {
+    v[j] = owner ? acc.d[j] : 0.0;
+    v[VEC + j] = owner ? acc.s[j] : 0.0;
+    v[2 * VEC + j] = owner ? acc.c[j] : 0.0;
   }
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < 3 * VEC; ++i)
 #pragma unroll
     for (int o = LPR; o < 32; o <<= 1) v[i] += __shfl_xor_sync(0xFFFFFFFFu, v[i], o);
   if (lane < LPR) {
-    sm[warp][2 * l8] = v[0];
-    sm[warp][2 * l8 + 1] = v[1];
-    sm[warp][TP + 2 * l8] = v[2];
-    sm[warp][TP + 2 * l8 + 1] = v[3];
-    sm[warp][2 * TP + 2 * l8] = v[4];
-    sm[warp][2 * TP + 2 * l8 + 1] = v[5];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      sm[warp][VEC * l8 + j] = v[j];
+      sm[warp][TP + VEC * l8 + j] = v[VEC + j];
+      sm[warp][2 * TP + VEC * l8 + j] = v[2 * VEC + j];
+    }
   }
   __syncthreads();
   if (threadIdx.x < 3 * TP) {
@@ -168,163 +224,182 @@ __device__ __forceinline__ void block_reduce(const SweepParams& p, Acc acc, bool
   }
 }
 
-// One gather step of an LPR-lane group: LPR source ids come from the group's
-// `idx` registers (lane j of the group holds edge j); all LPR row loads are
+// One gather step of an LPR-lane group: NJ source ids come from the `idx`
+// registers of lanes first_lane, first_lane + STRIDE, ...; all NJ row loads are
 // issued before any add so that they are in flight together.  Invalid slots
 // (kNone) load row 0 and add nothing.
-template <int LPR, int STRIDE>
+template <int LPR, int VEC, int NJ, int STRIDE>
 __device__ __forceinline__ void gather_step(const double* __restrict__ y, unsigned mask, uint32_t idx, int first_lane,
-                                            int l8, double& a0, double& a1) {
-  constexpr int TP = 2 * LPR;
-  double2 rows[LPR];
-  bool ok[LPR];
+                                            int l8, Vec<VEC>& a) {
+  constexpr int TP = LPR * VEC;
+  Vec<VEC> rows[NJ];
+  bool ok[NJ];
 #pragma unroll
-  for (int j = 0; j < LPR; ++j) {
+  for (int j = 0; j < NJ; ++j) {
     const uint32_t u = __shfl_sync(mask, idx, first_lane + j * STRIDE);
     ok[j] = u != kNone;
-    rows[j] = ld_row_gather(y + (uint64_t)(ok[j] ? u : 0u) * TP + 2 * l8);
+    rows[j] = ld_row_gather<VEC>(y + (uint64_t)(ok[j] ? u : 0u) * TP + VEC * l8);
   }
 #pragma unroll
-  for (int j = 0; j < LPR; ++j) {
-    a0 += ok[j] ? rows[j].x : 0.0;
-    a1 += ok[j] ? rows[j].y : 0.0;
-  }
+  for (int j = 0; j < NJ; ++j)
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) a.v[c] += ok[j] ? rows[j].v[c] : 0.0;
 }
 
 // Rows with in-degree <= kShortMax: one row per LPR-lane group, 32/LPR rows
-// per warp, consecutive rows in consecutive groups (coalesced y rows).  The
-// row pointers of the next row block and this row's own y/scale are fetched
-// before the gathers so that only index -> row remains a dependent chain.
-template <int LPR>
+// per warp, consecutive rows in consecutive groups (coalesced y rows).
+// Software pipeline over row blocks: the row pointers are fetched two blocks
+// ahead and the first LPR source ids one block ahead, and the row's own y/scale
+// before the gathers, so that only the row loads themselves are a dependent
+// round trip per block.
+template <int LPR, int VEC>
 __global__ void __launch_bounds__(kThreads, 4) k_sweep_short(SweepParams p, uint32_t n_row_blocks) {
-  constexpr int TP = 2 * LPR, GPW = 32 / LPR, GPC = GPW * (kThreads / 32);
+  constexpr int TP = LPR * VEC, GPW = 32 / LPR, GPC = GPW * (kThreads / 32);
   const int lane = threadIdx.x & 31, l8 = lane % LPR, g = lane / LPR;
   const unsigned gmask = (LPR == 32 ? 0xFFFFFFFFu : ((1u << LPR) - 1u)) << (g * LPR);
   const int group_in_cta = (threadIdx.x >> 5) * GPW + g;
-  Acc acc;
-  uint32_t rb = blockIdx.x;
-  uint64_t b_n = 0, e_n = 0;
-  {
+  Acc<VEC> acc;
+  auto load_ptr = [&](uint32_t rb, uint64_t& b, uint64_t& e) {
     const uint32_t r = rb * GPC + group_in_cta;
+    b = e = 0;
     if (rb < n_row_blocks && r < p.rows_loc) {
-      b_n = p.in_ptr[r];
-      e_n = p.in_ptr[r + 1];
+      b = p.in_ptr[r];
+      e = p.in_ptr[r + 1];
     }
-  }
+  };
+  auto first_ids = [&](uint64_t b, uint64_t e) -> uint32_t {
+    return (e - b <= kShortMax && b + l8 < e) ? __ldg(p.in_src + b + l8) : kNone;
+  };
+  uint32_t rb = blockIdx.x;
+  uint64_t b_c, e_c, b_n, e_n;
+  load_ptr(rb, b_c, e_c);
+  load_ptr(rb + gridDim.x, b_n, e_n);
+  uint32_t idx_c = first_ids(b_c, e_c);
   for (; rb < n_row_blocks; rb += gridDim.x) {
     const uint32_t r = rb * GPC + group_in_cta;
-    const uint64_t b = b_n, e = e_n;
-    {
-      const uint32_t rbn = rb + gridDim.x, rn = rbn * GPC + group_in_cta;
-      if (rbn < n_row_blocks && rn < p.rows_loc) {
-        b_n = p.in_ptr[rn];
-        e_n = p.in_ptr[rn + 1];
-      }
-    }
+    const uint64_t b = b_c, e = e_c;
+    uint32_t idx = idx_c;
+    b_c = b_n;
+    e_c = e_n;
+    load_ptr(rb + 2 * gridDim.x, b_n, e_n);
+    idx_c = first_ids(b_c, e_c);
     if (r >= p.rows_loc) continue;
     if (e - b > kShortMax) continue;  // a long row: k_sweep_long / k_sweep_fix own it
-    const double2 yl = ld_row_stream(p.y_last + (p.row_lo + r) * TP + 2 * l8);
+    const Vec<VEC> yl = ld_row_stream<VEC>(p.y_last + (p.row_lo + r) * TP + VEC * l8);
     const double m = p.mul[r];
-    double a0 = 0, a1 = 0;
+    Vec<VEC> a;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) a.v[c] = 0.0;
     for (uint64_t i = b; i < e; i += LPR) {
-      const uint32_t idx = (i + l8 < e) ? __ldg(p.in_src + i + l8) : kNone;
-      gather_step<LPR, 1>(p.y_last, gmask, idx, g * LPR, l8, a0, a1);
+      if (i != b) idx = (i + l8 < e) ? __ldg(p.in_src + i + l8) : kNone;
+      gather_step<LPR, VEC, LPR, 1>(p.y_last, gmask, idx, g * LPR, l8, a);
     }
-    epilogue<LPR>(p, r, l8, a0, a1, yl, m, acc);
+    epilogue<LPR, VEC>(p, r, l8, a, yl, m, acc);
   }
-  block_reduce<LPR>(p, acc, true);
+  block_reduce<LPR, VEC>(p, acc, true);
 }
 
 // Long-row tasks: one warp per task, 32 edges per step, group g takes edges
 // j*GPW+g; the GPW partial rows are combined with shuffles.  The next step's
 // indices are fetched before this step's rows.
-template <int LPR>
+template <int LPR, int VEC>
 __global__ void __launch_bounds__(kThreads, 4) k_sweep_long(SweepParams p, const LongTask* __restrict__ tasks,
                                                            uint32_t n_tasks, double* __restrict__ partials) {
-  constexpr int TP = 2 * LPR, GPW = 32 / LPR;
+  constexpr int TP = LPR * VEC, GPW = 32 / LPR;
   const int lane = threadIdx.x & 31, l8 = lane % LPR, g = lane / LPR;
   const uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * kThreads) >> 5;
-  Acc acc;
+  Acc<VEC> acc;
   for (uint32_t ti = warp; ti < n_tasks; ti += n_warps) {
     const LongTask t = tasks[ti];
     const uint32_t* src = p.in_src + t.e_begin;
-    double2 yl = make_double2(0, 0);
+    Vec<VEC> yl;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) yl.v[c] = 0.0;
     double m = 0;
     if (t.slot < 0 && g == 0) {
-      yl = ld_row_stream(p.y_last + (p.row_lo + t.row) * TP + 2 * l8);
+      yl = ld_row_stream<VEC>(p.y_last + (p.row_lo + t.row) * TP + VEC * l8);
       m = p.mul[t.row];
     }
-    double a0 = 0, a1 = 0;
+    Vec<VEC> a;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) a.v[c] = 0.0;
     uint32_t idx_next = lane < t.n ? __ldg(src + lane) : kNone;
     for (uint32_t i = 0; i < t.n; i += 32) {
       const uint32_t idx = idx_next;
       idx_next = (i + 32 + lane < t.n) ? __ldg(src + i + 32 + lane) : kNone;
-      gather_step<LPR, GPW>(p.y_last, 0xFFFFFFFFu, idx, g, l8, a0, a1);
+      gather_step<LPR, VEC, LPR, GPW>(p.y_last, 0xFFFFFFFFu, idx, g, l8, a);
     }
 #pragma unroll
-    for (int o = LPR; o < 32; o <<= 1) {
-      a0 += __shfl_xor_sync(0xFFFFFFFFu, a0, o);
-      a1 += __shfl_xor_sync(0xFFFFFFFFu, a1, o);
-    }
+    for (int o = LPR; o < 32; o <<= 1)
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) a.v[c] += __shfl_xor_sync(0xFFFFFFFFu, a.v[c], o);
     if (g == 0) {
       if (t.slot < 0) {
-        epilogue<LPR>(p, t.row, l8, a0, a1, yl, m, acc);
+        epilogue<LPR, VEC>(p, t.row, l8, a, yl, m, acc);
       } else {
-        *reinterpret_cast<double2*>(partials + (size_t)t.slot * TP + 2 * l8) = make_double2(a0, a1);
+        st_row_plain<VEC>(partials + (size_t)t.slot * TP + VEC * l8, a);
       }
     }
   }
-  block_reduce<LPR>(p, acc, g == 0);
+  block_reduce<LPR, VEC>(p, acc, g == 0);
 }
 
 // Rows that span several tasks: one CTA per row sums the partial rows in slot
 // order (fixed tree) and runs the epilogue.
-template <int LPR>
+template <int LPR, int VEC>
 __global__ void __launch_bounds__(kThreads) k_sweep_fix(SweepParams p, const FixRow* __restrict__ rows,
                                                        uint32_t n_fix, const double* __restrict__ partials) {
-  constexpr int TP = 2 * LPR, GPW = 32 / LPR, GPC = GPW * (kThreads / 32);
-  __shared__ double2 sm[kThreads / 32][LPR];
+  constexpr int TP = LPR * VEC, GPW = 32 / LPR, GPC = GPW * (kThreads / 32);
+  __shared__ double sm[kThreads / 32][16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l8 = lane % LPR, g = lane / LPR;
   const int group_in_cta = warp * GPW + g;
-  Acc acc;
+  Acc<VEC> acc;
   for (uint32_t fi = blockIdx.x; fi < n_fix; fi += gridDim.x) {
     const FixRow fr = rows[fi];
-    double2 yl = make_double2(0, 0);
+    Vec<VEC> yl;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) yl.v[c] = 0.0;
     double m = 0;
     if (warp == 0 && g == 0) {
-      yl = ld_row_stream(p.y_last + (p.row_lo + fr.row) * TP + 2 * l8);
+      yl = ld_row_stream<VEC>(p.y_last + (p.row_lo + fr.row) * TP + VEC * l8);
       m = p.mul[fr.row];
     }
-    double a0 = 0, a1 = 0;
+    Vec<VEC> a;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) a.v[c] = 0.0;
     for (uint32_t s = group_in_cta; s < fr.n_slots; s += GPC) {
-      const double2 v = *reinterpret_cast<const double2*>(partials + (size_t)(fr.first_slot + s) * TP + 2 * l8);
-      a0 += v.x;
-      a1 += v.y;
+      const Vec<VEC> v = ld_row_plain<VEC>(partials + (size_t)(fr.first_slot + s) * TP + VEC * l8);
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) a.v[c] += v.v[c];
     }
 #pragma unroll
-    for (int o = LPR; o < 32; o <<= 1) {
-      a0 += __shfl_xor_sync(0xFFFFFFFFu, a0, o);
-      a1 += __shfl_xor_sync(0xFFFFFFFFu, a1, o);
-    }
+    for (int o = LPR; o < 32; o <<= 1)
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) a.v[c] += __shfl_xor_sync(0xFFFFFFFFu, a.v[c], o);
     __syncthreads();  // sm reuse across iterations
-    if (g == 0) sm[warp][l8] = make_double2(a0, a1);
+    if (g == 0) {
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) sm[warp][VEC * l8 + c] = a.v[c];
+    }
     __syncthreads();
     if (warp == 0 && g == 0) {
-      double b0 = 0, b1 = 0;
+      Vec<VEC> b;
 #pragma unroll
-      for (int w = 0; w < kThreads / 32; ++w) {
-        b0 += sm[w][l8].x;
-        b1 += sm[w][l8].y;
+      for (int c = 0; c < VEC; ++c) {
+        double t = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) t += sm[w][VEC * l8 + c];
+        b.v[c] = t;
       }
-      epilogue<LPR>(p, fr.row, l8, b0, b1, yl, m, acc);
+      epilogue<LPR, VEC>(p, fr.row, l8, b, yl, m, acc);
     }
   }
-  block_reduce<LPR>(p, acc, warp == 0 && g == 0);
+  block_reduce<LPR, VEC>(p, acc, warp == 0 && g == 0);
 }
 
 // Two-stage fixed-order sum of the per-CTA partial rows: kReduceCtas CTAs each
-// fold a strided subset of the slots, then k_finish_tot folds those.
+// fold a strided subset of the slots, then k_fold_stage folds those.
 constexpr int kReduceCtas = 32;
 __global__ void __launch_bounds__(kThreads) k_reduce_partials(const double* __restrict__ red, uint32_t n_slots,
                                                               int width, double* __restrict__ stage) {
@@ -366,49 +441,52 @@ __global__ void k_fold_stage(const double* __restrict__ stage, int n_rows, int w
 __global__ void k_finish_tot(const double* __restrict__ sums, int TP, double tele, double n_nodes,
                              double* __restrict__ tot) {
   const int t = threadIdx.x;
-  if (t < TP) tot[t] = sums[TP + t] + tele * n_nodes;
+  if (t < TP) tot[t] = 1.0 / (sums[TP + t] + tele * n_nodes);  // the sweep multiplies by 1/Tot
 }
 
 // y0[v][t] = m(v) / n_t for every node (pagerank.go:101-107) and the partial
 // S_0 of this rank's rows.
-template <int LPR>
+template <int LPR, int VEC>
 __global__ void __launch_bounds__(kThreads) k_init(double* __restrict__ y, const uint32_t* __restrict__ outdeg,
                                                   uint64_t n_nodes, double damping, const double* __restrict__ init,
                                                   uint64_t row_lo, uint32_t rows_loc, double* __restrict__ mul_loc,
                                                   double* __restrict__ red) {
-  constexpr int TP = 2 * LPR;
+  constexpr int TP = LPR * VEC;
   __shared__ double sm[kThreads / 32][16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l8 = lane % LPR;
   const uint64_t n_groups = (uint64_t)gridDim.x * kThreads / LPR;
-  double s0 = 0, s1 = 0;
+  double s[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) s[c] = 0.0;
   for (uint64_t v = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) / LPR; v < n_nodes; v += n_groups) {
     const uint32_t od = outdeg[v];
     const double m = od ? damping / (double)od : 1.0;
-    const double2 val = make_double2(m * init[2 * l8], m * init[2 * l8 + 1]);
-    *reinterpret_cast<double2*>(y + v * TP + 2 * l8) = val;
+    Vec<VEC> val;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) val.v[c] = m * init[VEC * l8 + c];
+    st_row_plain<VEC>(y + v * TP + VEC * l8, val);
     if (v >= row_lo && v < row_lo + rows_loc) {
       if (l8 == 0) mul_loc[v - row_lo] = od ? m : 0.0;
       if (od) {
-        s0 += val.x;
-        s1 += val.y;
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) s[c] += val.v[c];
       }
     }
   }
 #pragma unroll
-  for (int o = LPR; o < 32; o <<= 1) {
-    s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, o);
-    s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o);
-  }
+  for (int o = LPR; o < 32; o <<= 1)
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) s[c] += __shfl_xor_sync(0xFFFFFFFFu, s[c], o);
   if (lane < LPR) {
-    sm[warp][2 * l8] = s0;
-    sm[warp][2 * l8 + 1] = s1;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) sm[warp][VEC * l8 + c] = s[c];
   }
   __syncthreads();
   if (threadIdx.x < 3 * TP) {
-    double s = 0;
+    double t = 0;
     if (threadIdx.x >= TP && threadIdx.x < 2 * TP)
-      for (int w = 0; w < kThreads / 32; ++w) s += sm[w][threadIdx.x - TP];
-    red[(size_t)blockIdx.x * 3 * TP + threadIdx.x] = s;
+      for (int w = 0; w < kThreads / 32; ++w) t += sm[w][threadIdx.x - TP];
+    red[(size_t)blockIdx.x * 3 * TP + threadIdx.x] = t;
   }
 }
 
@@ -556,21 +634,35 @@ void pagerank_state_free(PagerankState* s) {
   delete s;
 }
 
-static int lpr_for_topics(uint32_t T) {
-  if (T <= 2) return 1;
-  if (T <= 4) return 2;
-  if (T <= 8) return 4;
-  return 8;
+// Lane shape per padded topic count: (lanes per row, doubles per lane).
+// 128-bit accesses (vec 2) are the default: the sweep sits at the chip's row-gather
+// ceiling either way (scripts/bench_gather.cu) and the 256-bit shape spills its
+// twelve reduction accumulators.  SS_PR_VEC=4 selects the 256-bit shape for TP >= 8.
+struct Shape {
+  int lpr, vec;
+};
+static Shape shape_for_topics(uint32_t T) {
+  const char* env = getenv("SS_PR_VEC");
+  const bool wide = env && atoi(env) == 4;
+  if (T <= 2) return {1, 2};
+  if (T <= 4) return {2, 2};
+  if (T <= 8) return wide ? Shape{2, 4} : Shape{4, 2};
+  return wide ? Shape{4, 4} : Shape{8, 2};
 }
 
 template <class F>
-static int dispatch_lpr(int lpr, F&& f) {
-  switch (lpr) {
-    case 1: return f(std::integral_constant<int, 1>());
-    case 2: return f(std::integral_constant<int, 2>());
-    case 4: return f(std::integral_constant<int, 4>());
-    default: return f(std::integral_constant<int, 8>());
+static int dispatch_shape(Shape sh, F&& f) {
+  using std::integral_constant;
+  if (sh.vec == 2) {
+    switch (sh.lpr) {
+      case 1: return f(integral_constant<int, 1>(), integral_constant<int, 2>());
+      case 2: return f(integral_constant<int, 2>(), integral_constant<int, 2>());
+      case 4: return f(integral_constant<int, 4>(), integral_constant<int, 2>());
+      default: return f(integral_constant<int, 8>(), integral_constant<int, 2>());
+    }
   }
+  if (sh.lpr == 2) return f(integral_constant<int, 2>(), integral_constant<int, 4>());
+  return f(integral_constant<int, 4>(), integral_constant<int, 4>());
 }
 
 extern "C" {
@@ -754,7 +846,8 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
   }
   cudaStream_t st = e->stream;
   const int world = comm_world(e);
-  const int LPR = lpr_for_topics(n_topics), TP = 2 * LPR, T = (int)n_topics;
+  const Shape shape = shape_for_topics(n_topics);
+  const int LPR = shape.lpr, TP = shape.lpr * shape.vec, T = (int)n_topics;
   const uint64_t N = s->N;
   const uint32_t R = s->rows_loc;
   const bool timing = (e->flags & SS_FLAG_TIMING) != 0;
@@ -765,10 +858,10 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
   const int GPC = (32 / LPR) * (kThreads / 32);
   const uint32_t n_row_blocks = ss::div_up(R, GPC);
   int occ_short = 4, occ_long = 4;
-  dispatch_lpr(LPR, [&](auto lpr) {
-    constexpr int L = decltype(lpr)::value;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_short, k_sweep_short<L>, kThreads, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_long, k_sweep_long<L>, kThreads, 0);
+  dispatch_shape(shape, [&](auto lpr, auto vec) {
+    constexpr int L = decltype(lpr)::value, V = decltype(vec)::value;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_short, k_sweep_short<L, V>, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_long, k_sweep_long<L, V>, kThreads, 0);
     return SS_OK;
   });
   // persistent grids: exactly one resident wave, static block-cyclic work split
@@ -805,9 +898,9 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
   }
 
   // y0, mul, S_0
-  int rc = dispatch_lpr(LPR, [&](auto lpr) {
-    constexpr int L = decltype(lpr)::value;
-    k_init<L><<<grid_init, kThreads, 0, st>>>(s->y[0].p, s->outdeg.p, N, damping, s->init.p, s->row_lo, R, s->mul.p,
+  int rc = dispatch_shape(shape, [&](auto lpr, auto vec) {
+    constexpr int L = decltype(lpr)::value, V = decltype(vec)::value;
+    k_init<L, V><<<grid_init, kThreads, 0, st>>>(s->y[0].p, s->outdeg.p, N, damping, s->init.p, s->row_lo, R, s->mul.p,
                                              s->red.p);
     return SS_OK;
   });
@@ -830,7 +923,7 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
     p.in_ptr = s->in_ptr.p;
     p.in_src = s->in_src.p;
     p.mul = s->mul.p;
-    p.tot = s->tot.p;
+    p.inv_tot = s->tot.p;
     p.init = s->init.p;
     p.row_lo = s->row_lo;
     p.rows_loc = R;
@@ -838,16 +931,16 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
     p.tele = tele;
     p.first = sweep == 1;
     if (timing) SS_CUDA(cudaEventRecord(s->ev[0], st));
-    rc = dispatch_lpr(LPR, [&](auto lpr) {
-      constexpr int L = decltype(lpr)::value;
+    rc = dispatch_shape(shape, [&](auto lpr, auto vec) {
+      constexpr int L = decltype(lpr)::value, V = decltype(vec)::value;
       SweepParams q = p;
       q.red = s->red.p;
-      k_sweep_short<L><<<grid_short, kThreads, 0, st>>>(q, n_row_blocks);
+      k_sweep_short<L, V><<<grid_short, kThreads, 0, st>>>(q, n_row_blocks);
       q.red = s->red.p + (size_t)grid_short * W;
-      k_sweep_long<L><<<grid_long, kThreads, 0, st>>>(q, s->tasks.p, s->n_tasks, s->partials.p);
+      k_sweep_long<L, V><<<grid_long, kThreads, 0, st>>>(q, s->tasks.p, s->n_tasks, s->partials.p);
       if (timing) cudaEventRecord(s->ev[1], st);
       q.red = s->red.p + (size_t)(grid_short + grid_long) * W;
-      k_sweep_fix<L><<<grid_fix, kThreads, 0, st>>>(q, s->fix.p, s->n_fix, s->partials.p);
+      k_sweep_fix<L, V><<<grid_fix, kThreads, 0, st>>>(q, s->fix.p, s->n_fix, s->partials.p);
       return SS_OK;
     });
     SS_TRY(rc);
