@@ -67,6 +67,12 @@ struct DevBuf {
     n = count;
     return SS_OK;
   }
+  // grow-only: keeps the block when it is already large enough (cudaMalloc/cudaFree of
+  // gigabyte blocks costs tens to hundreds of milliseconds and synchronises the device)
+  int reserve(size_t count) {
+    if (p && n >= count) return SS_OK;
+    return alloc(count + count / 8);
+  }
   size_t bytes() const { return n * sizeof(T); }
 };
 

@@ -508,24 +508,37 @@ __global__ void k_outdeg(const uint64_t* __restrict__ row_ptr, uint64_t n, uint3
   const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (u < n) outdeg[u] = (uint32_t)(row_ptr[u + 1] - row_ptr[u]);
 }
-// src[e] = the row that owns out-edge e; in-degree histogram of the children.
-__global__ void k_expand_src(const uint64_t* __restrict__ row_ptr, uint64_t n, uint64_t n_edges,
-                             const uint32_t* __restrict__ col_idx, uint32_t* __restrict__ src,
-                             unsigned long long* __restrict__ indeg, int* __restrict__ bad) {
-  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_edges) return;
-  uint64_t lo = 0, hi = n;  // last u with row_ptr[u] <= e
+// src[e] = the row that owns out-edge e, four consecutive edges per thread (one
+// binary search, then a walk over the row boundaries); children validated.
+__global__ void k_expand_src4(const uint64_t* __restrict__ row_ptr, uint64_t n, uint64_t n_edges,
+                              const uint32_t* __restrict__ col_idx, uint32_t* __restrict__ src,
+                              int* __restrict__ bad) {
+  const uint64_t e0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (e0 >= n_edges) return;
+  uint64_t lo = 0, hi = n;  // last u with row_ptr[u] <= e0
   while (hi - lo > 1) {
     const uint64_t mid = (lo + hi) >> 1;
-    if (row_ptr[mid] <= e) lo = mid; else hi = mid;
+    if (row_ptr[mid] <= e0) lo = mid; else hi = mid;
   }
-  src[e] = (uint32_t)lo;
-  const uint32_t c = col_idx[e];
-  if (c >= n) {
-    *bad = 1;
-    return;
+  uint64_t u = lo, next = row_ptr[u + 1];
+  const uint64_t e1 = min(n_edges, e0 + 4);
+  for (uint64_t e = e0; e < e1; ++e) {
+    while (e >= next) next = row_ptr[++u + 1];
+    src[e] = (uint32_t)u;
+    if (col_idx[e] >= n) *bad = 1;
   }
-  atomicAdd(indeg + c + 1, 1ull);
+}
+// in_ptr[v] = first position of child v in the child-sorted edge list
+__global__ void k_in_ptr_from_sorted(const uint32_t* __restrict__ dst_sorted, uint64_t n_edges, uint64_t n,
+                                     unsigned long long* __restrict__ in_ptr) {
+  const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v > n) return;
+  uint64_t lo = 0, hi = n_edges;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (dst_sorted[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  in_ptr[v] = lo;
 }
 __global__ void k_check_row_ptr(const uint64_t* __restrict__ row_ptr, uint64_t n, uint64_t n_edges,
                                 int* __restrict__ bad) {
@@ -605,6 +618,7 @@ __global__ void k_gather_tasks(const LongTask* __restrict__ in, const uint32_t* 
 }  // namespace
 
 struct PagerankState {
+  bool loaded = false;
   uint64_t N = 0, E = 0;
   uint64_t row_lo = 0;
   uint32_t rows_loc = 0;
@@ -621,15 +635,27 @@ struct PagerankState {
   double damping = 0;
   ss::DevBuf<double> y[2];
   int cur = 0;  // y[cur] holds the latest ranks
-  ss::DevBuf<double> mul, partials, red, stage, sums, tot, init;
+  ss::DevBuf<double> mul, partials, red, stage, sums, tot, init, out_stage[2];
   bool have_result = false;
   ss_pagerank_stats stats{};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t out_ev[2] = {nullptr, nullptr};
+  // load-time scratch, kept between loads (grow-only)
+  struct Scratch {
+    ss::DevBuf<uint64_t> row_ptr;
+    ss::DevBuf<uint32_t> col, src, col_sorted, src_sorted, nt, nf, toff, foff, keys, keys_out, order, order_out;
+    ss::DevBuf<unsigned long long> in_ptr_full, bounds;
+    ss::DevBuf<int> bad;
+    ss::DevBuf<char> tmp;
+    ss::DevBuf<LongTask> unsorted;
+  } sc;
 };
 
 void pagerank_state_free(PagerankState* s) {
   if (!s) return;
   for (auto& e : s->ev)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : s->out_ev)
     if (e) cudaEventDestroy(e);
   delete s;
 }
@@ -675,144 +701,129 @@ SS_API int ss_graph_load_csr(ss_engine* e, uint64_t n_nodes, uint64_t n_edges, c
   std::lock_guard<std::mutex> lock(e->mu);
   DeviceGuard guard(e->device);
   auto t_begin = std::chrono::steady_clock::now();
-  pagerank_state_free(e->pr);
-  e->pr = nullptr;
-  PagerankState* s = new (std::nothrow) PagerankState();
-  SS_REQUIRE(s, SS_ERR_OOM, "host allocation failed");
-  struct Cleanup {
-    PagerankState*& s;
-    ~Cleanup() { if (s) pagerank_state_free(s); }
-  } cleanup{s};
+  if (!e->pr) {
+    e->pr = new (std::nothrow) PagerankState();
+    SS_REQUIRE(e->pr, SS_ERR_OOM, "host allocation failed");
+    for (auto& ev : e->pr->ev) SS_CUDA(cudaEventCreate(&ev));
+    for (auto& ev : e->pr->out_ev) SS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  PagerankState* s = e->pr;  // device blocks are reused across loads
+  PagerankState::Scratch& sc = s->sc;
+  s->loaded = false;
+  s->have_result = false;
 
   cudaStream_t st = e->stream;
   const uint64_t N = n_nodes, E = n_edges;
   const int world = comm_world(e), rank = comm_rank(e);
+  SS_REQUIRE(world < 64, SS_ERR_INVALID, "world size %d too large", world);
   s->N = N;
   s->E = E;
   s->bounds.assign(world + 1, 0);
 
-  ss::DevBuf<uint64_t> d_row_ptr;
-  ss::DevBuf<uint32_t> d_col, d_src, d_col_sorted, d_src_sorted;
-  ss::DevBuf<unsigned long long> d_in_ptr_full, d_bounds;
-  ss::DevBuf<int> d_bad;
-  SS_TRY(d_row_ptr.alloc(N + 1));
-  SS_TRY(d_col.alloc(E));
-  SS_TRY(d_src.alloc(E));
-  SS_TRY(d_in_ptr_full.alloc(N + 2));
-  SS_TRY(d_bounds.alloc(world + 1));
-  SS_TRY(d_bad.alloc(1));
-  SS_TRY(s->outdeg.alloc(N));
-  SS_CUDA(cudaMemcpyAsync(d_row_ptr.p, row_ptr, (N + 1) * 8, cudaMemcpyHostToDevice, st));
-  if (E) SS_CUDA(cudaMemcpyAsync(d_col.p, col_idx, E * 4, cudaMemcpyHostToDevice, st));
-  SS_CUDA(cudaMemsetAsync(d_in_ptr_full.p, 0, (N + 2) * 8, st));
-  SS_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
+  SS_TRY(sc.row_ptr.reserve(N + 1));
+  SS_TRY(sc.col.reserve(E));
+  SS_TRY(sc.src.reserve(E));
+  SS_TRY(sc.col_sorted.reserve(E));
+  SS_TRY(sc.src_sorted.reserve(E));
+  SS_TRY(sc.in_ptr_full.reserve(N + 2));
+  SS_TRY(sc.bounds.reserve(world + 1));
+  SS_TRY(sc.bad.reserve(1));
+  SS_TRY(s->outdeg.reserve(N));
+  SS_CUDA(cudaMemcpyAsync(sc.row_ptr.p, row_ptr, (N + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (E) SS_CUDA(cudaMemcpyAsync(sc.col.p, col_idx, E * 4, cudaMemcpyHostToDevice, st));
+  SS_CUDA(cudaMemsetAsync(sc.bad.p, 0, sizeof(int), st));
   if (N) {
-    k_check_row_ptr<<<ss::div_up(N, 256), 256, 0, st>>>(d_row_ptr.p, N, E, d_bad.p);
-    k_outdeg<<<ss::div_up(N, 256), 256, 0, st>>>(d_row_ptr.p, N, s->outdeg.p);
+    k_check_row_ptr<<<ss::div_up(N, 256), 256, 0, st>>>(sc.row_ptr.p, N, E, sc.bad.p);
+    k_outdeg<<<ss::div_up(N, 256), 256, 0, st>>>(sc.row_ptr.p, N, s->outdeg.p);
   }
-  if (E) k_expand_src<<<ss::div_up(E, 256), 256, 0, st>>>(d_row_ptr.p, N, E, d_col.p, d_src.p, d_in_ptr_full.p, d_bad.p);
   int bad = 0;
-  SS_CUDA(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(&bad, sc.bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaStreamSynchronize(st));
-  SS_REQUIRE(!bad, SS_ERR_INVALID, "ss_graph_load_csr: row_ptr not monotone / child id out of range");
+  SS_REQUIRE(!bad, SS_ERR_INVALID, "ss_graph_load_csr: row_ptr not monotone or row_ptr[n] != n_edges");
+  if (E) k_expand_src4<<<ss::div_up(ss::div_up(E, 4), 256), 256, 0, st>>>(sc.row_ptr.p, N, E, sc.col.p, sc.src.p, sc.bad.p);
+  SS_CUDA(cudaMemcpyAsync(&bad, sc.bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
 
-  // in_ptr_full = inclusive scan of the shifted histogram (slot v+1 holds indeg(v))
-  {
+  // sort edges by child (stable: parents stay ascending inside a row)
+  if (E) {
+    int end_bit = 1;
+    while ((1ull << end_bit) < N) ++end_bit;
     size_t tmp_bytes = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, d_in_ptr_full.p, d_in_ptr_full.p, (int64_t)(N + 1), st);
-    ss::DevBuf<char> tmp;
-    SS_TRY(tmp.alloc(tmp_bytes));
-    SS_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, d_in_ptr_full.p, d_in_ptr_full.p, (int64_t)(N + 1), st));
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, sc.col.p, sc.col_sorted.p, sc.src.p, sc.src_sorted.p,
+                                    (int64_t)E, 0, end_bit, st);
+    SS_TRY(sc.tmp.reserve(tmp_bytes));
+    tmp_bytes = sc.tmp.n;
+    SS_CUDA(cub::DeviceRadixSort::SortPairs(sc.tmp.p, tmp_bytes, sc.col.p, sc.col_sorted.p, sc.src.p,
+                                            sc.src_sorted.p, (int64_t)E, 0, end_bit, st));
   }
-  SS_REQUIRE(world < 64, SS_ERR_INVALID, "world size %d too large", world);
-  k_partition<<<1, 64, 0, st>>>(d_in_ptr_full.p, N, world, d_bounds.p);
+  k_in_ptr_from_sorted<<<ss::div_up(N + 1, 256), 256, 0, st>>>(sc.col_sorted.p, E, N, sc.in_ptr_full.p);
+  k_partition<<<1, 64, 0, st>>>(sc.in_ptr_full.p, N, world, sc.bounds.p);
   std::vector<unsigned long long> hb(world + 1);
-  SS_CUDA(cudaMemcpyAsync(hb.data(), d_bounds.p, (world + 1) * 8, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(hb.data(), sc.bounds.p, (world + 1) * 8, cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaStreamSynchronize(st));
+  SS_REQUIRE(!bad, SS_ERR_INVALID, "ss_graph_load_csr: child id out of range");
   for (int r = 0; r <= world; ++r) s->bounds[r] = hb[r];
   s->row_lo = s->bounds[rank];
   s->rows_loc = (uint32_t)(s->bounds[rank + 1] - s->bounds[rank]);
 
-  // sort edges by child (stable: parents stay ascending inside a row)
   unsigned long long e_lo = 0, e_hi = 0;
-  SS_CUDA(cudaMemcpyAsync(&e_lo, d_in_ptr_full.p + s->row_lo, 8, cudaMemcpyDeviceToHost, st));
-  SS_CUDA(cudaMemcpyAsync(&e_hi, d_in_ptr_full.p + s->row_lo + s->rows_loc, 8, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(&e_lo, sc.in_ptr_full.p + s->row_lo, 8, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(&e_hi, sc.in_ptr_full.p + s->row_lo + s->rows_loc, 8, cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaStreamSynchronize(st));
   s->E_loc = e_hi - e_lo;
-  SS_TRY(s->in_src.alloc(s->E_loc));
-  if (E) {
-    SS_TRY(d_col_sorted.alloc(E));
-    SS_TRY(d_src_sorted.alloc(E));
-    int end_bit = 1;
-    while ((1ull << end_bit) < N) ++end_bit;
-    size_t tmp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_col.p, d_col_sorted.p, d_src.p, d_src_sorted.p,
-                                    (int64_t)E, 0, end_bit, st);
-    ss::DevBuf<char> tmp;
-    SS_TRY(tmp.alloc(tmp_bytes));
-    SS_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, d_col.p, d_col_sorted.p, d_src.p, d_src_sorted.p,
-                                            (int64_t)E, 0, end_bit, st));
-    if (s->E_loc)
-      SS_CUDA(cudaMemcpyAsync(s->in_src.p, d_src_sorted.p + e_lo, s->E_loc * 4, cudaMemcpyDeviceToDevice, st));
-  }
-  SS_TRY(s->in_ptr.alloc((size_t)s->rows_loc + 1));
-  k_local_ptr<<<ss::div_up((uint64_t)s->rows_loc + 1, 256), 256, 0, st>>>(d_in_ptr_full.p, s->row_lo, s->rows_loc,
+  SS_TRY(s->in_src.reserve(s->E_loc));
+  if (s->E_loc)
+    SS_CUDA(cudaMemcpyAsync(s->in_src.p, sc.src_sorted.p + e_lo, s->E_loc * 4, cudaMemcpyDeviceToDevice, st));
+  SS_TRY(s->in_ptr.reserve((size_t)s->rows_loc + 1));
+  k_local_ptr<<<ss::div_up((uint64_t)s->rows_loc + 1, 256), 256, 0, st>>>(sc.in_ptr_full.p, s->row_lo, s->rows_loc,
                                                                          s->in_ptr.p);
-  SS_CUDA(cudaStreamSynchronize(st));
-  d_col.reset();
-  d_src.reset();
-  d_col_sorted.reset();
-  d_src_sorted.reset();
-  d_row_ptr.reset();
 
   // long-row tasks and fix rows
+  s->n_tasks = s->n_fix = 0;
   if (s->rows_loc) {
     const uint32_t R = s->rows_loc;
-    ss::DevBuf<uint32_t> nt, nf, toff, foff;
-    SS_TRY(nt.alloc((size_t)R + 1));
-    SS_TRY(nf.alloc((size_t)R + 1));
-    SS_TRY(toff.alloc((size_t)R + 1));
-    SS_TRY(foff.alloc((size_t)R + 1));
-    SS_CUDA(cudaMemsetAsync(nt.p, 0, ((size_t)R + 1) * 4, st));
-    SS_CUDA(cudaMemsetAsync(nf.p, 0, ((size_t)R + 1) * 4, st));
-    k_count_tasks<<<ss::div_up(R, 256), 256, 0, st>>>(s->in_ptr.p, R, nt.p, nf.p);
+    SS_TRY(sc.nt.reserve((size_t)R + 1));
+    SS_TRY(sc.nf.reserve((size_t)R + 1));
+    SS_TRY(sc.toff.reserve((size_t)R + 1));
+    SS_TRY(sc.foff.reserve((size_t)R + 1));
+    SS_CUDA(cudaMemsetAsync(sc.nt.p + R, 0, 4, st));
+    SS_CUDA(cudaMemsetAsync(sc.nf.p + R, 0, 4, st));
+    k_count_tasks<<<ss::div_up(R, 256), 256, 0, st>>>(s->in_ptr.p, R, sc.nt.p, sc.nf.p);
     size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, nt.p, toff.p, (int)(R + 1), st);
-    ss::DevBuf<char> tmp;
-    SS_TRY(tmp.alloc(tmp_bytes));
-    SS_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, nt.p, toff.p, (int)(R + 1), st));
-    SS_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, nf.p, foff.p, (int)(R + 1), st));
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, sc.nt.p, sc.toff.p, (int)(R + 1), st);
+    SS_TRY(sc.tmp.reserve(tmp_bytes));
+    tmp_bytes = sc.tmp.n;
+    SS_CUDA(cub::DeviceScan::ExclusiveSum(sc.tmp.p, tmp_bytes, sc.nt.p, sc.toff.p, (int)(R + 1), st));
+    tmp_bytes = sc.tmp.n;
+    SS_CUDA(cub::DeviceScan::ExclusiveSum(sc.tmp.p, tmp_bytes, sc.nf.p, sc.foff.p, (int)(R + 1), st));
     uint32_t n_tasks = 0, n_fix = 0;
-    SS_CUDA(cudaMemcpyAsync(&n_tasks, toff.p + R, 4, cudaMemcpyDeviceToHost, st));
-    SS_CUDA(cudaMemcpyAsync(&n_fix, foff.p + R, 4, cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaMemcpyAsync(&n_tasks, sc.toff.p + R, 4, cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaMemcpyAsync(&n_fix, sc.foff.p + R, 4, cudaMemcpyDeviceToHost, st));
     SS_CUDA(cudaStreamSynchronize(st));
     s->n_tasks = n_tasks;
     s->n_fix = n_fix;
     if (n_tasks) {
-      ss::DevBuf<LongTask> unsorted;
-      ss::DevBuf<uint32_t> keys, keys_out, order, order_out;
-      SS_TRY(unsorted.alloc(n_tasks));
-      SS_TRY(s->tasks.alloc(n_tasks));
-      SS_TRY(s->fix.alloc(n_fix));
-      SS_TRY(keys.alloc(n_tasks));
-      SS_TRY(keys_out.alloc(n_tasks));
-      SS_TRY(order.alloc(n_tasks));
-      SS_TRY(order_out.alloc(n_tasks));
-      k_fill_tasks<<<ss::div_up(R, 256), 256, 0, st>>>(s->in_ptr.p, s->in_src.p, R, nt.p, toff.p, foff.p,
-                                                       unsorted.p, keys.p, order.p, s->fix.p);
+      SS_TRY(sc.unsorted.reserve(n_tasks));
+      SS_TRY(s->tasks.reserve(n_tasks));
+      SS_TRY(s->fix.reserve(n_fix));
+      SS_TRY(sc.keys.reserve(n_tasks));
+      SS_TRY(sc.keys_out.reserve(n_tasks));
+      SS_TRY(sc.order.reserve(n_tasks));
+      SS_TRY(sc.order_out.reserve(n_tasks));
+      k_fill_tasks<<<ss::div_up(R, 256), 256, 0, st>>>(s->in_ptr.p, s->in_src.p, R, sc.nt.p, sc.toff.p, sc.foff.p,
+                                                       sc.unsorted.p, sc.keys.p, sc.order.p, s->fix.p);
       size_t sort_bytes = 0;
-      cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys.p, keys_out.p, order.p, order_out.p, (int)n_tasks,
-                                      0, 32, st);
-      ss::DevBuf<char> sort_tmp;
-      SS_TRY(sort_tmp.alloc(sort_bytes));
-      SS_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp.p, sort_bytes, keys.p, keys_out.p, order.p, order_out.p,
-                                              (int)n_tasks, 0, 32, st));
-      k_gather_tasks<<<ss::div_up(n_tasks, 256), 256, 0, st>>>(unsorted.p, order_out.p, n_tasks, s->tasks.p);
-      SS_CUDA(cudaStreamSynchronize(st));
+      cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, sc.keys.p, sc.keys_out.p, sc.order.p, sc.order_out.p,
+                                      (int)n_tasks, 0, 32, st);
+      SS_TRY(sc.tmp.reserve(sort_bytes));
+      sort_bytes = sc.tmp.n;
+      SS_CUDA(cub::DeviceRadixSort::SortPairs(sc.tmp.p, sort_bytes, sc.keys.p, sc.keys_out.p, sc.order.p,
+                                              sc.order_out.p, (int)n_tasks, 0, 32, st));
+      k_gather_tasks<<<ss::div_up(n_tasks, 256), 256, 0, st>>>(sc.unsorted.p, sc.order_out.p, n_tasks, s->tasks.p);
     }
   }
+  SS_CUDA(cudaStreamSynchronize(st));
   SS_CUDA(cudaGetLastError());
-  for (auto& ev : s->ev) SS_CUDA(cudaEventCreate(&ev));
+  s->stats = ss_pagerank_stats{};
   s->stats.n_nodes = N;
   s->stats.n_edges = E;
   s->stats.row_lo = s->row_lo;
@@ -820,8 +831,7 @@ SS_API int ss_graph_load_csr(ss_engine* e, uint64_t n_nodes, uint64_t n_edges, c
   s->stats.local_edges = s->E_loc;
   s->stats.load_ms =
       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
-  e->pr = s;
-  s = nullptr;  // ownership moved
+  s->loaded = true;
   return SS_OK;
 }
 
@@ -831,7 +841,7 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
   std::lock_guard<std::mutex> lock(e->mu);
   DeviceGuard guard(e->device);
   PagerankState* s = e->pr;
-  SS_REQUIRE(s, SS_ERR_STATE, "ss_pagerank: no graph loaded");
+  SS_REQUIRE(s && s->loaded, SS_ERR_STATE, "ss_pagerank: no graph loaded");
   SS_REQUIRE(n_topics == 0 || num_pages, SS_ERR_INVALID, "ss_pagerank: num_pages is NULL");
   SS_REQUIRE(n_topics <= 16, SS_ERR_INVALID,
              "ss_pagerank: %u topics; run topics in slabs of <= 16 (they are independent)", n_topics);
@@ -874,17 +884,15 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
   const uint32_t red_slots = std::max(grid_short + grid_long + grid_fix, grid_init);
   const int W = 3 * TP;
 
-  if (s->y[0].n != N * TP) {
-    SS_TRY(s->y[0].alloc(N * TP));
-    SS_TRY(s->y[1].alloc(N * TP));
-  }
-  if (s->mul.n != std::max<size_t>(R, 1)) SS_TRY(s->mul.alloc(R));
-  if (s->partials.n != std::max<size_t>((size_t)s->n_tasks * TP, 1)) SS_TRY(s->partials.alloc((size_t)s->n_tasks * TP));
-  if (s->red.n != (size_t)red_slots * W) SS_TRY(s->red.alloc((size_t)red_slots * W));
-  if (s->sums.n != (size_t)W) SS_TRY(s->sums.alloc(W));
-  if (s->stage.n != (size_t)kReduceCtas * W) SS_TRY(s->stage.alloc((size_t)kReduceCtas * W));
-  if (s->tot.n != (size_t)TP) SS_TRY(s->tot.alloc(TP));
-  if (s->init.n != (size_t)TP) SS_TRY(s->init.alloc(TP));
+  SS_TRY(s->y[0].reserve(N * TP));
+  SS_TRY(s->y[1].reserve(N * TP));
+  SS_TRY(s->mul.reserve(R));
+  SS_TRY(s->partials.reserve((size_t)s->n_tasks * TP));
+  SS_TRY(s->red.reserve((size_t)red_slots * W));
+  SS_TRY(s->sums.reserve(W));
+  SS_TRY(s->stage.reserve((size_t)kReduceCtas * W));
+  SS_TRY(s->tot.reserve(TP));
+  SS_TRY(s->init.reserve(TP));
 
   double h_init[16];
   for (int t = 0; t < TP; ++t) h_init[t] = t < T ? 1.0 / (double)num_pages[t] : 0.0;  // pagerank.go:104
@@ -988,8 +996,8 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
     // the state is replicated on every rank after the exchange: unscale all rows
     // in bounded chunks and copy them out
     const uint64_t chunk_rows = std::max<uint64_t>(1, (64ull << 20) / ((uint64_t)T * 8));
-    ss::DevBuf<double> stage;
-    SS_TRY(stage.alloc(std::min<uint64_t>(chunk_rows, N) * T));
+    ss::DevBuf<double>& stage = s->out_stage[0];
+    SS_TRY(stage.reserve(std::min<uint64_t>(chunk_rows, N) * T));
     for (uint64_t lo = 0; lo < N; lo += chunk_rows) {
       const uint64_t hi = std::min<uint64_t>(lo + chunk_rows, N);
       const uint64_t total = (hi - lo) * T;
@@ -1013,8 +1021,8 @@ SS_API int ss_pagerank_fetch(ss_engine* e, uint64_t row_lo, uint64_t row_hi, dou
   cudaStream_t st = e->stream;
   const int T = s->T;
   const uint64_t chunk_rows = std::max<uint64_t>(1, (64ull << 20) / ((uint64_t)T * 8));
-  ss::DevBuf<double> stage;
-  SS_TRY(stage.alloc(std::min<uint64_t>(chunk_rows, row_hi - row_lo) * T));
+  ss::DevBuf<double>& stage = s->out_stage[0];
+  SS_TRY(stage.reserve(std::min<uint64_t>(chunk_rows, row_hi - row_lo) * T));
   for (uint64_t lo = row_lo; lo < row_hi; lo += chunk_rows) {
     const uint64_t hi = std::min<uint64_t>(lo + chunk_rows, row_hi);
     const uint64_t total = (hi - lo) * T;
