@@ -32,7 +32,8 @@ namespace {
 
 constexpr int kT = 256;        // threads per CTA
 constexpr int kRange = 2048;   // docs per sub-range
-constexpr int kCand = 1024;    // doc slots finished per candidate round
+constexpr int kCand = 1024;    // candidate buffer = doc slots finished per round
+constexpr int kBatch = kCand;  // doc slots fetched together in the finalize step
 constexpr int kMaxK = 128;
 constexpr int kMaxKw = 64;     // keyword tokens per query handled in-kernel
 constexpr int kMaxPh = 32;     // phrase tokens per query handled in-kernel
@@ -112,6 +113,7 @@ struct Smem {
   uint32_t n_cand, n_ent, top_n, top_buf;
   unsigned long long thr_key, piv_key;
   uint32_t thr_doc, piv_doc;
+  float thr_f;  // fp32 lower bound of the k-th best score (-inf until k results exist)
 };
 
 // Union of the running top-k and the candidate buffer -> new running top-k by
@@ -179,6 +181,9 @@ __device__ void merge_candidates(Smem& s, uint32_t k) {
     if (s.top_n == k) {
       s.thr_key = s.top_key[nb][k - 1];
       s.thr_doc = s.top_doc[nb][k - 1];
+      const double thr = key_score(s.thr_key);
+      // NaN as k-th best (only NaN scores so far) must not filter anything
+      s.thr_f = isnan(thr) ? -__int_as_float(0x7f800000) : __double2float_rd(thr);
     }
   }
   __syncthreads();
@@ -285,6 +290,18 @@ __device__ __forceinline__ DocMeta load_meta(const ScoreParams& p, uint32_t q, u
 // make the top k goes to the candidate buffer.
 __device__ __forceinline__ void finish_doc(Smem& s, uint64_t doc, double tr, double br, const DocMeta& m, double qm,
                                            uint32_t k) {
+  // Cheap rejection first: once k results exist, a doc whose score -- evaluated in fp32 with a
+  // margin far above fp32 rounding error -- stays below the running k-th best cannot enter the
+  // top k, so its exact score is never needed.  NaN/Inf fall through to the exact path.
+  if (s.top_n >= k) {
+    const float qf = (float)qm;
+    const float a = 0.33f * (float)m.sqd;
+    const float b = tr != 0.0 ? 0.38f * __fdividef((float)tr, (float)m.mag_t * qf) : 0.0f;
+    const float c = br != 0.0 ? 0.29f * __fdividef((float)br, (float)m.mag_b * qf) : 0.0f;
+    const float approx = (a + b + c) * 100.0f;
+    const float slack = (fabsf(a) + fabsf(b) + fabsf(c)) * 1e-2f + 1e-30f;  // 1e-4 relative, x100
+    if (approx + slack < s.thr_f) return;
+  }
   // get_metadata.go:57-66.  x/y with x == 0 is 0 or NaN, and NaN becomes 0: skip the divide
   double body = 0.0, title = 0.0;
   if (br != 0.0) {
@@ -412,7 +429,7 @@ __device__ void sort_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
   }
 }
 
-__global__ void __launch_bounds__(kT) k_score(ScoreParams p) {
+__global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   const uint32_t q = blockIdx.x % p.n_q, slab = blockIdx.x / p.n_q;  // slab-major launch order
@@ -435,6 +452,7 @@ __global__ void __launch_bounds__(kT) k_score(ScoreParams p) {
     s.top_buf = 0;
     s.thr_key = 0;
     s.thr_doc = kNoDoc;
+    s.thr_f = -__int_as_float(0x7f800000);
   }
   // narrow every list to the slab
   for (uint32_t l = tid; l < n_lists; l += kT) {
@@ -489,51 +507,62 @@ __global__ void __launch_bounds__(kT) k_score(ScoreParams p) {
   __syncthreads();
   for (uint32_t sj = 0; sj < nb; ++sj) {
     const uint64_t d0 = slab_lo + (uint64_t)(sub0 + sj) * kRange;
-    for (uint32_t l = tid; l < n_lists; l += kT) {
-      s.cur[l] = s.base[l] + s.bounds[l * (nb + 1) + sj];
-      s.hi[l] = s.base[l] + s.bounds[l * (nb + 1) + sj + 1];
-    }
-    __syncthreads();
+    // list l covers postings [base + bounds[l][sj], base + bounds[l][sj+1]) in this sub-range
+    auto lo_of = [&](uint32_t l) { return s.base[l] + s.bounds[l * (nb + 1) + sj]; };
+    auto hi_of = [&](uint32_t l) { return s.base[l] + s.bounds[l * (nb + 1) + sj + 1]; };
 
-    // keyword tokens in query order (duplicates count again)
+    // keyword tokens in query order (duplicates count again); a barrier only after a token
+    // that touched the accumulators
     bool any = false;
     for (uint32_t i = 0; i < n_kw; ++i) {
-      const unsigned long long t0 = s.cur[2 * i], t1 = s.hi[2 * i], b0 = s.cur[2 * i + 1], b1 = s.hi[2 * i + 1];
+      const unsigned long long t0 = lo_of(2 * i), t1 = hi_of(2 * i), b0 = lo_of(2 * i + 1), b1 = hi_of(2 * i + 1);
       if (t1 == t0 && b1 == b0) continue;
+      if (any) __syncthreads();  // the previous token's updates are complete
       any = true;
       accumulate_list(p.tab[1], s, 1, b0, b1, d0);
       accumulate_list(p.tab[0], s, 0, t0, t1, d0);
       if (tid == 0) n_postings += (t1 - t0) + (b1 - b0);
-      __syncthreads();
     }
     // the phrase's weight is appended after the keyword weights (main_retrieve.go:73-78)
     if (n_ph) {
       bool ph_any = false;
-      for (uint32_t i = 0; i < 2 * n_ph; ++i) ph_any |= s.hi[2 * n_kw + i] != s.cur[2 * n_kw + i];
+      for (uint32_t i = 0; i < 2 * n_ph; ++i) ph_any |= hi_of(2 * n_kw + i) != lo_of(2 * n_kw + i);
       if (ph_any) {
+        if (any) __syncthreads();
+        for (uint32_t l = 2 * n_kw + tid; l < n_lists; l += kT) {
+          s.cur[l] = lo_of(l);
+          s.hi[l] = hi_of(l);
+        }
+        __syncthreads();
         any = true;
         apply_phrase<false>(p, s, 1, 2 * n_kw, n_ph, d0, 0, n_postings);
         apply_phrase<false>(p, s, 0, 2 * n_kw, n_ph, d0, 0, n_postings);
-        __syncthreads();
       }
     }
+    if (!any) continue;  // uniform
+    __syncthreads();
 
-    if (any) {
-      // finish the matched docs, word by word of the bitmap (work follows the matches);
-      // a lane's docs of one round are fetched together before any of them is scored
-      const uint32_t lane = tid & 31, warp = tid >> 5;
-      constexpr int kWordsPerWarp = kCand / 32 / (kT / 32);
-      for (uint32_t w0 = 0; w0 < kRange / 32; w0 += kCand / 32) {
-        bool has[kWordsPerWarp];
-        uint32_t slot[kWordsPerWarp];
-        DocMeta meta[kWordsPerWarp];
-        double tr[kWordsPerWarp], br[kWordsPerWarp];
+    // finish the matched docs, word by word of the bitmap (work follows the matches);
+    // a lane's docs of one batch are fetched together before any of them is scored
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    constexpr int kWordsPerWarp = kBatch / 32 / (kT / 32);
+    for (uint32_t w0 = 0; w0 < kRange / 32; w0 += kBatch / 32) {
+      bool has[kWordsPerWarp];
+      uint32_t slot[kWordsPerWarp];
+      DocMeta meta[kWordsPerWarp];
+      double tr[kWordsPerWarp], br[kWordsPerWarp];
+      uint32_t any_word = 0;
+#pragma unroll
+      for (int r = 0; r < kWordsPerWarp; ++r) {
+        const uint32_t wi = w0 + warp + r * (kT / 32);
+        const uint32_t word = s.bits[wi];
+        any_word |= word;
+        has[r] = (word >> lane) & 1u;
+        slot[r] = wi * 32 + lane;
+      }
+      if (any_word) {  // warp uniform: something matched in this warp's words
 #pragma unroll
         for (int r = 0; r < kWordsPerWarp; ++r) {
-          const uint32_t wi = w0 + warp + r * (kT / 32);
-          const uint32_t word = s.bits[wi];
-          has[r] = (word >> lane) & 1u;
-          slot[r] = wi * 32 + lane;
           meta[r] = load_meta(p, q, d0 + (has[r] ? slot[r] : 0u));
           tr[r] = s.acc[0][slot[r]];
           br[r] = s.acc[1][slot[r]];
@@ -548,11 +577,16 @@ __global__ void __launch_bounds__(kT) k_score(ScoreParams p) {
           ++n_matched;
           finish_doc(s, d0 + slot[r], tr[r], br[r], meta[r], qm, k);
         }
+      }
+      if (kBatch < kRange) {  // the candidate buffer holds one batch: merge between batches
         __syncthreads();
         if (s.n_cand) merge_candidates(s, k);
       }
     }
-    __syncthreads();
+    if (kBatch >= kRange) {
+      __syncthreads();  // accumulators and bitmap are clean again; candidates are complete
+      if (s.n_cand) merge_candidates(s, k);
+    }
   }
   }
   }
