@@ -12,3 +12,6 @@ int comm_allreduce_sum_f64(ss_engine* e, double* dev_buf, size_t count);
 // every rank r contributes dev_buf[byte_off[r] .. +byte_cnt[r]) of a buffer that
 // has the same layout on all ranks (rank blocks of the PageRank state)
 int comm_allgatherv_bytes(ss_engine* e, void* dev_buf, const size_t* byte_off, const size_t* byte_cnt);
+// every rank contributes `bytes` bytes; out receives world * bytes (host buffers, small payloads:
+// staged through device memory and NCCL)
+int comm_allgather_host_bytes(ss_engine* e, const void* in, size_t bytes, void* out);

@@ -114,6 +114,24 @@ int comm_allgatherv_bytes(ss_engine* e, void* dev_buf, const size_t* byte_off, c
   return SS_OK;
 }
 
+int comm_allgather_host_bytes(ss_engine* e, const void* in, size_t bytes, void* out) {
+  const int world = comm_world(e);
+  if (world == 1) {
+    memcpy(out, in, bytes);
+    return SS_OK;
+  }
+  auto* api = ss::nccl_api();
+  SS_REQUIRE(api && api->AllGather, SS_ERR_NCCL, "libnccl not loadable");
+  ss::DevBuf<char> d_in, d_out;
+  SS_TRY(d_in.alloc(bytes));
+  SS_TRY(d_out.alloc(bytes * world));
+  SS_CUDA(cudaMemcpyAsync(d_in.p, in, bytes, cudaMemcpyHostToDevice, e->stream));
+  SS_NCCL(api, api->AllGather(d_in.p, d_out.p, bytes, ncclChar, e->comm->comm, e->stream));
+  SS_CUDA(cudaMemcpyAsync(out, d_out.p, bytes * world, cudaMemcpyDeviceToHost, e->stream));
+  SS_CUDA(cudaStreamSynchronize(e->stream));
+  return SS_OK;
+}
+
 extern "C" {
 
 SS_API int ss_version(void) { return 100; }

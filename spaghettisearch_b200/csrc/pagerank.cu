@@ -57,9 +57,12 @@ struct FixRow {
   uint32_t row, first_slot, n_slots, pad;
 };
 
+constexpr int kMaxPeers = 7;  // fused exchange up to 8 GPUs
 struct SweepParams {
   const double* y_last;
   double* y_next;
+  double* peer_next[kMaxPeers];  // the same y_next buffer on the other ranks (peer memory), fused exchange
+  int n_peers;
   const uint64_t* in_ptr;   // [rows_loc + 1], offsets into in_src
   const uint32_t* in_src;   // sources ascending within a row
   const double* mul;        // [rows_loc] d/out, or 0 for dangling rows
@@ -187,6 +190,10 @@ __device__ __forceinline__ void epilogue(const SweepParams& p, uint32_t r, int l
     if (has_out) acc.s[j] += yn.v[j];
   }
   st_row_stream<VEC>(p.y_next + v * TP + VEC * l8, yn);
+  // Fused exchange: the finished row goes straight into every peer's copy of y_next over
+  // NVLink (posted stores), overlapping the transfer with the rest of the sweep instead of
+  // an all-gather afterwards.
+  for (int q = 0; q < p.n_peers; ++q) st_row_plain<VEC>(p.peer_next[q] + v * TP + VEC * l8, yn);
 }
 
 // CTA-wide fixed-shape reduction of the per-thread sums into red[blockIdx.x].
@@ -296,6 +303,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_sweep_short(SweepParams p, uint
     }
     epilogue<LPR, VEC>(p, r, l8, a, yl, m, acc);
   }
+  if (p.n_peers) __threadfence_system();  // pushed rows are performed before the kernel retires
   block_reduce<LPR, VEC>(p, acc, true);
 }
 
@@ -342,6 +350,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_sweep_long(SweepParams p, const
       }
     }
   }
+  if (p.n_peers) __threadfence_system();
   block_reduce<LPR, VEC>(p, acc, g == 0);
 }
 
@@ -395,6 +404,7 @@ __global__ void __launch_bounds__(kThreads) k_sweep_fix(SweepParams p, const Fix
       epilogue<LPR, VEC>(p, fr.row, l8, b, yl, m, acc);
     }
   }
+  if (p.n_peers) __threadfence_system();
   block_reduce<LPR, VEC>(p, acc, warp == 0 && g == 0);
 }
 
@@ -640,6 +650,11 @@ struct PagerankState {
   ss_pagerank_stats stats{};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t out_ev[2] = {nullptr, nullptr};
+  // fused exchange over peer memory (CUDA IPC): peers' y[0]/y[1]
+  bool fused = false;
+  int n_peers = 0;
+  double* peer_y[2][kMaxPeers] = {};
+  void* y_base_exported[2] = {nullptr, nullptr};
   // load-time scratch, kept between loads (grow-only)
   struct Scratch {
     ss::DevBuf<uint64_t> row_ptr;
@@ -651,8 +666,77 @@ struct PagerankState {
   } sc;
 };
 
+static void close_peers(PagerankState* s) {
+  for (int b = 0; b < 2; ++b)
+    for (int q = 0; q < kMaxPeers; ++q)
+      if (s->peer_y[b][q]) {
+        cudaIpcCloseMemHandle(s->peer_y[b][q]);
+        s->peer_y[b][q] = nullptr;
+      }
+  s->fused = false;
+  s->n_peers = 0;
+}
+
+// Map every peer's y buffers into this process (CUDA IPC) so that the sweep epilogue can
+// push finished rows directly.  Handles travel through the engine's own NCCL communicator.
+static int open_peers(ss_engine* e, PagerankState* s) {
+  const int world = comm_world(e), rank = comm_rank(e);
+  if (s->fused && s->y_base_exported[0] == s->y[0].p && s->y_base_exported[1] == s->y[1].p) return SS_OK;
+  close_peers(s);
+  if (world == 1 || world > kMaxPeers + 1) return SS_OK;
+  if (const char* env = getenv("SS_PR_EXCHANGE"))
+    if (!strcmp(env, "nccl")) return SS_OK;
+  struct Pack {
+    cudaIpcMemHandle_t h[2];
+    int device;
+  } mine{}, all[kMaxPeers + 1];
+  SS_CUDA(cudaIpcGetMemHandle(&mine.h[0], s->y[0].p));
+  SS_CUDA(cudaIpcGetMemHandle(&mine.h[1], s->y[1].p));
+  mine.device = e->device;
+  SS_TRY(comm_allgather_host_bytes(e, &mine, sizeof(Pack), all));
+  int q = 0;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) continue;
+    for (int b = 0; b < 2; ++b) {
+      void* ptr = nullptr;
+      cudaError_t err = cudaIpcOpenMemHandle(&ptr, all[r].h[b], cudaIpcMemLazyEnablePeerAccess);
+      if (err != cudaSuccess) {  // no peer path: fall back to the NCCL exchange
+        cudaGetLastError();
+        close_peers(s);
+        return SS_OK;
+      }
+      s->peer_y[b][q] = (double*)ptr;
+    }
+    ++q;
+  }
+  s->n_peers = q;
+  s->fused = true;
+  s->y_base_exported[0] = s->y[0].p;
+  s->y_base_exported[1] = s->y[1].p;
+  return SS_OK;
+}
+
+// Every rank must take the same exchange path: fused only if all ranks mapped all peers.
+static int agree_on_fused(ss_engine* e, PagerankState* s) {
+  const int world = comm_world(e);
+  if (world == 1) return SS_OK;
+  SS_TRY(s->sums.reserve(1));
+  const double mine = s->fused ? 1.0 : 0.0;
+  double total = 0;
+  SS_CUDA(cudaMemcpyAsync(s->sums.p, &mine, 8, cudaMemcpyHostToDevice, e->stream));
+  SS_TRY(comm_allreduce_sum_f64(e, s->sums.p, 1));
+  SS_CUDA(cudaMemcpyAsync(&total, s->sums.p, 8, cudaMemcpyDeviceToHost, e->stream));
+  SS_CUDA(cudaStreamSynchronize(e->stream));
+  if (total != (double)world && s->fused) {
+    close_peers(s);
+    s->y_base_exported[0] = s->y_base_exported[1] = nullptr;
+  }
+  return SS_OK;
+}
+
 void pagerank_state_free(PagerankState* s) {
   if (!s) return;
+  close_peers(s);
   for (auto& e : s->ev)
     if (e) cudaEventDestroy(e);
   for (auto& e : s->out_ev)
@@ -884,8 +968,15 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
   const uint32_t red_slots = std::max(grid_short + grid_long + grid_fix, grid_init);
   const int W = 3 * TP;
 
-  SS_TRY(s->y[0].reserve(N * TP));
-  SS_TRY(s->y[1].reserve(N * TP));
+  if (world > 1) {  // fixed-size state so that the peer mappings survive topic-count changes
+    SS_TRY(s->y[0].reserve(N * 16));
+    SS_TRY(s->y[1].reserve(N * 16));
+    SS_TRY(open_peers(e, s));
+    SS_TRY(agree_on_fused(e, s));
+  } else {
+    SS_TRY(s->y[0].reserve(N * TP));
+    SS_TRY(s->y[1].reserve(N * TP));
+  }
   SS_TRY(s->mul.reserve(R));
   SS_TRY(s->partials.reserve((size_t)s->n_tasks * TP));
   SS_TRY(s->red.reserve((size_t)red_slots * W));
@@ -938,6 +1029,8 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
     p.active_mask = active;
     p.tele = tele;
     p.first = sweep == 1;
+    p.n_peers = s->fused ? s->n_peers : 0;
+    for (int q = 0; q < kMaxPeers; ++q) p.peer_next[q] = s->fused ? s->peer_y[s->cur ^ 1][q] : nullptr;
     if (timing) SS_CUDA(cudaEventRecord(s->ev[0], st));
     rc = dispatch_shape(shape, [&](auto lpr, auto vec) {
       constexpr int L = decltype(lpr)::value, V = decltype(vec)::value;
@@ -956,7 +1049,9 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
     k_fold_stage<<<1, 64, 0, st>>>(s->stage.p, kReduceCtas, W, s->sums.p);
     if (timing) SS_CUDA(cudaEventRecord(s->ev[2], st));
     if (world > 1) {
-      SS_TRY(comm_allgatherv_bytes(e, p.y_next, byte_off.data(), byte_cnt.data()));
+      // fused: rows were pushed by the epilogue; the all-reduce below doubles as the barrier that
+      // orders every rank's pushes before anybody's next sweep
+      if (!s->fused) SS_TRY(comm_allgatherv_bytes(e, p.y_next, byte_off.data(), byte_cnt.data()));
       SS_TRY(comm_allreduce_sum_f64(e, s->sums.p, W));
     }
     k_finish_tot<<<1, 32, 0, st>>>(s->sums.p, TP, tele, (double)N, s->tot.p);
