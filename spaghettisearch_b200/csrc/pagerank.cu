@@ -684,8 +684,13 @@ static int open_peers(ss_engine* e, PagerankState* s) {
   if (s->fused && s->y_base_exported[0] == s->y[0].p && s->y_base_exported[1] == s->y[1].p) return SS_OK;
   close_peers(s);
   if (world == 1 || world > kMaxPeers + 1) return SS_OK;
-  if (const char* env = getenv("SS_PR_EXCHANGE"))
-    if (!strcmp(env, "nccl")) return SS_OK;
+  // Measured on 8 B200s (profiles/r01_multigpu.txt): with one peer the pushed rows ride along
+  // for free (2 GPUs: 658 -> 870 GTEPS), but seven 128-byte remote stores per row throttle the
+  // whole sweep (70 ms vs 5 ms + 14.5 ms NCCL).  Default: fused for 2 ranks, NCCL beyond;
+  // SS_PR_EXCHANGE=fused|nccl overrides.
+  const char* env = getenv("SS_PR_EXCHANGE");
+  if (env && !strcmp(env, "nccl")) return SS_OK;
+  if (world > 2 && !(env && !strcmp(env, "fused"))) return SS_OK;
   struct Pack {
     cudaIpcMemHandle_t h[2];
     int device;
