@@ -37,6 +37,10 @@ struct IndexState {
   ss::DevBuf<double> sqd;
   std::vector<double> sqd_probs;
   bool sqd_valid = false;
+  // packed fp32 screening record per doc (score.cu), rebuilt when norms / blend inputs change
+  ss::DevBuf<float4> meta32;
+  bool meta32_valid = false;
+  int meta32_mode = -1;
   ss_score_stats stats{};
   // grow-only device workspace of ss_score_batch (cudaMalloc/cudaFree per batch would
   // synchronise the device and dominate small batches)

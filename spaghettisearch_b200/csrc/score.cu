@@ -53,6 +53,7 @@ struct TableView {
 struct ScoreParams {
   TableView tab[2];      // 0 = title, 1 = body
   const double* mag[2];
+  const float4* meta32;  // [D] {1/mag_title, 1/mag_body, blend bound, 0} in fp32 for the screening pass
   const double* sqd;     // [D] blend term for a shared topic vector, or NULL
   const double* pr;      // [D][T] for per-query topic vectors
   const double* probs;   // [n_q][T] when per-query
@@ -267,7 +268,7 @@ __device__ void apply_phrase(const ScoreParams& p, Smem& s, int tb, uint32_t l0,
   }
 }
 
-// Per-doc inputs of the final rank, fetched together so that their latencies overlap.
+// Exact per-doc inputs of the final rank (only docs that survive the screening need them).
 struct DocMeta {
   double mag_t, mag_b, sqd;
 };
@@ -288,20 +289,24 @@ __device__ __forceinline__ DocMeta load_meta(const ScoreParams& p, uint32_t q, u
 
 // cosine, NaN -> 0, PageRank blend (get_metadata.go:53-69); a doc that can still
 // make the top k goes to the candidate buffer.
-__device__ __forceinline__ void finish_doc(Smem& s, uint64_t doc, double tr, double br, const DocMeta& m, double qm,
-                                           uint32_t k) {
-  // Cheap rejection first: once k results exist, a doc whose score -- evaluated in fp32 with a
-  // margin far above fp32 rounding error -- stays below the running k-th best cannot enter the
-  // top k, so its exact score is never needed.  NaN/Inf fall through to the exact path.
+//
+// Screening first: once k results exist, a doc whose score -- bounded from one packed fp32
+// record (reciprocal norms, blend bound) with a margin far above fp32 rounding -- stays below
+// the running k-th best cannot enter the top k, so its exact fp64 inputs are never fetched.
+// blend_scale = 1 for a shared topic vector (the record holds sqd itself) or sum |p_t| for a
+// per-query vector (the record holds max_t |PR[doc][t]|).  NaN/Inf fall through to the exact path.
+__device__ __forceinline__ void finish_doc(const ScoreParams& p, Smem& s, uint32_t q, uint64_t doc, double tr,
+                                           double br, const float4& m32, float qf_inv, float blend_scale,
+                                           double qm, uint32_t k) {
   if (s.top_n >= k) {
-    const float qf = (float)qm;
-    const float a = 0.33f * (float)m.sqd;
-    const float b = tr != 0.0 ? 0.38f * __fdividef((float)tr, (float)m.mag_t * qf) : 0.0f;
-    const float c = br != 0.0 ? 0.29f * __fdividef((float)br, (float)m.mag_b * qf) : 0.0f;
+    const float a = 0.33f * m32.z * blend_scale;
+    const float b = tr != 0.0 ? 0.38f * ((float)tr * m32.x * qf_inv) : 0.0f;
+    const float c = br != 0.0 ? 0.29f * ((float)br * m32.y * qf_inv) : 0.0f;
     const float approx = (a + b + c) * 100.0f;
     const float slack = (fabsf(a) + fabsf(b) + fabsf(c)) * 1e-2f + 1e-30f;  // 1e-4 relative, x100
     if (approx + slack < s.thr_f) return;
   }
+  const DocMeta m = load_meta(p, q, doc);
   // get_metadata.go:57-66.  x/y with x == 0 is 0 or NaN, and NaN becomes 0: skip the divide
   double body = 0.0, title = 0.0;
   if (br != 0.0) {
@@ -353,7 +358,8 @@ __device__ __forceinline__ void accumulate_list(const TableView& tv, Smem& s, in
 // tagged (doc offset, list sequence, weight), sorted, and every doc's run is folded in
 // sequence order -- the same sums as the dense path without touching empty sub-ranges.
 __device__ void sort_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t slab_lo, uint32_t n_kw, uint32_t n_ph,
-                          double qm, uint32_t k, unsigned long long& n_postings, unsigned long long& n_matched) {
+                          double qm, float qf_inv, float blend_scale, uint32_t k, unsigned long long& n_postings,
+                          unsigned long long& n_matched) {
   unsigned long long* ent = reinterpret_cast<unsigned long long*>(&s.acc[0][0]);
   const uint32_t tid = threadIdx.x, n_kw_lists = 2 * n_kw;
   if (tid == 0) {
@@ -421,8 +427,7 @@ __device__ void sort_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
         if ((e >> 32) & 1ull) br = __dadd_rn(br, w); else tr = __dadd_rn(tr, w);
       }
       ++n_matched;
-      const DocMeta m = load_meta(p, q, slab_lo + off);
-      finish_doc(s, slab_lo + off, tr, br, m, qm, k);
+      finish_doc(p, s, q, slab_lo + off, tr, br, p.meta32[slab_lo + off], qf_inv, blend_scale, qm, k);
     }
     __syncthreads();
     if (s.n_cand) merge_candidates(s, k);
@@ -479,12 +484,19 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
     work += mn;  // a phrase can hit at most once per posting of its shortest list
   }
   const double qm = sqrt((double)q_len);  // get_metadata.go:53
+  const float qf_inv = 1.0f / (float)qm;
+  float blend_scale = 1.0f;  // screening: |sum_t p_t PR_t| <= (sum_t |p_t|) * max_t |PR_t|
+  if (p.probs) {
+    blend_scale = 0.0f;
+    for (uint32_t t = 0; t < p.T; ++t) blend_scale += fabsf((float)p.probs[(uint64_t)q * p.T + t]);
+    blend_scale *= 1.0001f;
+  }
   unsigned long long n_postings = 0, n_matched = 0;
 
   if (work == 0) {
     // nothing of this query lives in this slab
   } else if (work <= kSortMax && p.slab_docs <= (1ull << 24)) {
-    sort_path(p, s, q, slab_lo, n_kw, n_ph, qm, k, n_postings, n_matched);
+    sort_path(p, s, q, slab_lo, n_kw, n_ph, qm, qf_inv, blend_scale, k, n_postings, n_matched);
   } else {
   for (uint32_t i = tid; i < kRange; i += kT) {
     s.acc[0][i] = 0.0;
@@ -549,7 +561,7 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
     for (uint32_t w0 = 0; w0 < kRange / 32; w0 += kBatch / 32) {
       bool has[kWordsPerWarp];
       uint32_t slot[kWordsPerWarp];
-      DocMeta meta[kWordsPerWarp];
+      float4 meta[kWordsPerWarp];
       double tr[kWordsPerWarp], br[kWordsPerWarp];
       uint32_t any_word = 0;
 #pragma unroll
@@ -563,7 +575,7 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
       if (any_word) {  // warp uniform: something matched in this warp's words
 #pragma unroll
         for (int r = 0; r < kWordsPerWarp; ++r) {
-          meta[r] = load_meta(p, q, d0 + (has[r] ? slot[r] : 0u));
+          meta[r] = p.meta32[d0 + (has[r] ? slot[r] : 0u)];
           tr[r] = s.acc[0][slot[r]];
           br[r] = s.acc[1][slot[r]];
         }
@@ -575,7 +587,7 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
           s.acc[0][slot[r]] = 0.0;
           s.acc[1][slot[r]] = 0.0;
           ++n_matched;
-          finish_doc(s, d0 + slot[r], tr[r], br[r], meta[r], qm, k);
+          finish_doc(p, s, q, d0 + slot[r], tr[r], br[r], meta[r], qf_inv, blend_scale, qm, k);
         }
       }
       if (kBatch < kRange) {  // the candidate buffer holds one batch: merge between batches
@@ -682,6 +694,28 @@ __global__ void k_sqd(const double* __restrict__ pr, const double* __restrict__ 
   sqd[d] = acc;
 }
 
+// Screening record per doc: fp32 reciprocals of the two norms and the blend term (shared
+// topic vector: sqd itself; per-query vectors: max_t |PR[doc][t]|; no blend: 0).
+__global__ void k_meta32(const double* __restrict__ mag_t, const double* __restrict__ mag_b,
+                         const double* __restrict__ sqd, const double* __restrict__ pr, uint32_t T, uint64_t D,
+                         float4* __restrict__ out) {
+  const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float4 m;
+  m.x = 1.0f / (float)mag_t[d];
+  m.y = 1.0f / (float)mag_b[d];
+  m.z = 0.0f;
+  if (sqd) {
+    m.z = (float)sqd[d];
+  } else if (pr) {
+    float mx = 0.0f;
+    for (uint32_t t = 0; t < T; ++t) mx = fmaxf(mx, fabsf((float)pr[d * T + t]) * 1.0001f);
+    m.z = mx;
+  }
+  m.w = 0.0f;
+  out[d] = m;
+}
+
 TableView view_of(const TableState& tb) {
   TableView v{};
   if (!tb.loaded) return v;
@@ -785,6 +819,10 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
                 memcmp(ix->sqd_probs.data(), topic_probs, ix->T * 8) == 0;
     if (!sqd_fresh && ix->sqd.n < std::max<uint64_t>(D, 1)) SS_TRY(ix->sqd.alloc(D));
   }
+  if (ix->meta32.n < std::max<uint64_t>(D, 1)) {
+    SS_TRY(ix->meta32.alloc(D));
+    ix->meta32_valid = false;
+  }
   if (timing)
     for (auto& x : ws.ev)
       if (!x) SS_CUDA(cudaEventCreate(&x));
@@ -814,11 +852,27 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
     SS_CUDA(cudaMemcpyAsync(ws.probs.p, topic_probs, n_q * ix->T * 8, cudaMemcpyHostToDevice, st));
   }
 
+  const double* mag0 = ix->tab[0].loaded ? ix->tab[0].mag.p : ws.zero_mag.p;
+  const double* mag1 = ix->tab[1].loaded ? ix->tab[1].mag.p : ws.zero_mag.p;
+  {
+    // rebuilt whenever its inputs may have changed (cheap: one pass over D docs)
+    const int mode = !blend ? 0 : (probs_per_query ? 2 : 1);
+    const bool fresh = ix->meta32_valid && ix->meta32_mode == mode && (mode != 1 || sqd_fresh);
+    if (!fresh) {
+      if (D) k_meta32<<<ss::div_up(D, 256), 256, 0, st>>>(mag0, mag1, mode == 1 ? ix->sqd.p : nullptr,
+                                                          mode == 2 ? ix->pr.p : nullptr, ix->T, D, ix->meta32.p);
+      ++launches;
+      ix->meta32_valid = true;
+      ix->meta32_mode = mode;
+    }
+  }
+
   ScoreParams p{};
+  p.meta32 = ix->meta32.p;
   p.tab[0] = view_of(ix->tab[0]);
   p.tab[1] = view_of(ix->tab[1]);
-  p.mag[0] = ix->tab[0].loaded ? ix->tab[0].mag.p : ws.zero_mag.p;
-  p.mag[1] = ix->tab[1].loaded ? ix->tab[1].mag.p : ws.zero_mag.p;
+  p.mag[0] = mag0;
+  p.mag[1] = mag1;
   p.sqd = sqd_ptr;
   p.pr = (blend && probs_per_query) ? ix->pr.p : nullptr;
   p.probs = (blend && probs_per_query) ? ws.probs.p : nullptr;
