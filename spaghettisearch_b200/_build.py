@@ -4,6 +4,7 @@ Artefacts land next to this file so that they travel to the GPU box with the
 repo snapshot:
   libspaghetti_gpu.so  the product: CUDA kernels + the C ABI of include/spaghetti.h
   libss_synth.so       synthetic workload generators
+  libspaghetti_host.so C++ mirror of the Go API over table snapshots, calls the C ABI
 """
 from __future__ import annotations
 
@@ -18,6 +19,7 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 GPU_LIB = PKG / "libspaghetti_gpu.so"
 SYNTH_LIB = PKG / "libss_synth.so"
+HOST_LIB = PKG / "libspaghetti_host.so"
 
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -79,8 +81,18 @@ def build_gpu(force: bool = False, verbose: bool = False, ptxas_info: bool = Fal
     return GPU_LIB
 
 
+def build_host(force: bool = False, verbose: bool = False) -> Path:
+    """C++ mirror of the reference's Go API over table snapshots (csrc/host), on top of the C ABI."""
+    srcs = [CSRC / "host" / "host_mirror.cpp", CSRC / "host" / "host_mirror.h", ROOT / "include" / "spaghetti.h"]
+    build_gpu(force=False, verbose=verbose)
+    if force or _stale(HOST_LIB, srcs + [GPU_LIB]):
+        _run([_host_cxx(), "-O2", "-std=c++17", "-fPIC", "-Wall", "-fvisibility=hidden", "-shared", "-I", ROOT / "include",
+              "-o", HOST_LIB, srcs[0], "-L", PKG, "-lspaghetti_gpu", "-Wl,-rpath,$ORIGIN"], verbose)
+    return HOST_LIB
+
+
 def build_all(force: bool = False, verbose: bool = False):
-    return build_synth(force, verbose), build_gpu(force, verbose)
+    return build_synth(force, verbose), build_gpu(force, verbose), build_host(force, verbose)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,179 @@
+"""C++ host mirror of the Go API over table snapshots.
+
+CPU part: the reference's JSON value encodings round-trip and forw[2] exports to the CSR the
+engine expects.  GPU part: UpdateTopicSensitivePagerank / UpdateTermWeights / Retrieve over
+snapshots against the oracle on the equivalent dense arrays."""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+
+from oracle import loader as O
+from spaghettisearch_b200 import host, synth
+
+
+def md5(s):
+    return hashlib.md5(s.encode()).hexdigest()  # indexer/indexer.go:38-39,366-367
+
+
+def make_tables(tmp_path, n_nodes=400, n_edges=4000, n_terms=120, cats=5):
+    """Synthetic crawl written in the reference's table formats; returns paths + dense views."""
+    g = synth.graph(n_nodes, n_edges, seed=3)
+    doc_key = [md5(f"http://site/{i}") for i in range(n_nodes)]
+    # forw[2] has a row only for crawled pages (those with children here); others appear as children only
+    rows2 = []
+    for u in range(n_nodes):
+        kids = g.col_idx[g.row_ptr[u]:g.row_ptr[u + 1]]
+        if len(kids):
+            rows2.append((doc_key[u], [doc_key[c] for c in kids]))
+    rows2.append((md5("http://site/uncrawled-null"), None))  # a row whose value is JSON null
+    host.write_jsonl(tmp_path / "forw2.jsonl", rows2)
+    host.write_jsonl(tmp_path / "forw5.jsonl",
+                     [(f"Top{c}", {"numPages": 50000 + 12345 * c, "wordCount": 1000 + c}) for c in range(cats)])
+    tabs = {}
+    for name, tid in (("inv0", 0), ("inv1", 1)):
+        t = synth.index_table(n_terms, n_nodes, tid, with_positions=True, seed=5)
+        rows = []
+        for term in range(n_terms):
+            a, b = int(t.term_ptr[term]), int(t.term_ptr[term + 1])
+            if a == b:
+                continue
+            val = {}
+            for p in range(a, b):
+                pos = t.pos[int(t.pos_ptr[p]):int(t.pos_ptr[p + 1])]
+                val[doc_key[t.doc_ids[p]]] = [float(t.norm_tf[p])] + [float(x) for x in pos]
+            rows.append((md5(f"term{term}"), val))
+        host.write_jsonl(tmp_path / f"{name}.jsonl", rows)
+        tabs[name] = t
+    return g, doc_key, tabs
+
+
+def test_codecs_and_graph_export(built, tmp_path):
+    g, doc_key, tabs = make_tables(tmp_path)
+    db = host.DB()
+    try:
+        for t in ("forw2", "forw5", "inv0", "inv1"):
+            db.load(t, tmp_path / f"{t}.jsonl")
+        assert db.rows("forw5") == 5 and db.rows("inv1") > 0
+        # values survive a load/save cycle (float32 weights and positions included)
+        for t in ("forw2", "forw5", "inv0", "inv1"):
+            db.save(t, tmp_path / f"{t}.out.jsonl")
+            a, b = host.read_jsonl(tmp_path / f"{t}.jsonl"), host.read_jsonl(tmp_path / f"{t}.out.jsonl")
+            assert a.keys() == b.keys()
+            for k in a:
+                if t.startswith("inv"):
+                    assert a[k].keys() == b[k].keys()
+                    for d in a[k]:
+                        assert np.array_equal(np.float32(a[k][d]), np.float32(b[k][d]))
+                else:
+                    assert a[k] == b[k]
+        # CSR export: node set = keys U children, ids = rank of the hex hash (pagerank.go:24-44)
+        db.export_graph(tmp_path / "graph.bin")
+        raw = (tmp_path / "graph.bin").read_bytes()
+        n, e = np.frombuffer(raw, np.uint64, 2)
+        row_ptr = np.frombuffer(raw, np.uint64, int(n) + 1, 16)
+        col = np.frombuffer(raw, np.uint32, int(e), 16 + 8 * (int(n) + 1))
+        keys = raw[16 + 8 * (int(n) + 1) + 4 * int(e):].decode().split()
+        nodes = set(doc_key[u] for u in range(len(doc_key)) if g.row_ptr[u + 1] > g.row_ptr[u])
+        nodes |= set(doc_key[c] for c in g.col_idx) | {md5("http://site/uncrawled-null")}
+        assert keys == sorted(nodes) and int(e) == g.n_edges
+        kid = {k: i for i, k in enumerate(keys)}
+        for u in (0, 7, 123):
+            exp = [kid[doc_key[c]] for c in g.col_idx[g.row_ptr[u]:g.row_ptr[u + 1]]]
+            i = kid.get(doc_key[u])
+            if i is not None:
+                assert col[int(row_ptr[i]):int(row_ptr[i + 1])].tolist() == exp
+    finally:
+        db.close()
+
+
+def test_bad_json_is_an_error(built, tmp_path):
+    (tmp_path / "bad.jsonl").write_text('{"k": "abc", "v": {"not": "a list"}}\n')
+    (tmp_path / "broken.jsonl").write_text('{"k": "abc", "v": [1, 2}\n')
+    (tmp_path / "f5.jsonl").write_text('{"k": "Top", "v": {"numPages": 10}}\n')
+    db = host.DB()
+    try:
+        db.load("forw2", tmp_path / "bad.jsonl")  # raw value kept; decoding happens on use
+        db.load("forw5", tmp_path / "f5.jsonl")
+        with pytest.raises(host.HostError):
+            db.export_graph(tmp_path / "g.bin")  # the reference panics on json.Unmarshal errors (pagerank.go:28-30)
+        with pytest.raises(host.HostError):
+            db.load("nosuch", tmp_path / "f5.jsonl")
+        with pytest.raises(host.HostError):
+            db.load("forw2", tmp_path / "broken.jsonl")
+    finally:
+        db.close()
+
+
+@pytest.mark.gpu
+def test_go_api_over_snapshots(engine, tmp_path):
+    g, doc_key, tabs = make_tables(tmp_path)
+    db = host.DB()
+    try:
+        for t in ("forw2", "forw5", "inv0", "inv1"):
+            db.load(t, tmp_path / f"{t}.jsonl")
+        # ---- ranking.UpdateTopicSensitivePagerank (start_crawl.go:175 uses eps 1e-20; 1e-12 here so that
+        # sweep counts are comparable)
+        db.update_pagerank(engine, 0.75, 1e-12)
+        db.save("forw3", tmp_path / "forw3.jsonl")
+        f3 = host.read_jsonl(tmp_path / "forw3.jsonl")
+        keys = sorted(f3)
+        kid = {k: i for i, k in enumerate(keys)}
+        # oracle on the same dense graph
+        n = len(keys)
+        rows = [[] for _ in range(n)]
+        for u in range(len(doc_key)):
+            if doc_key[u] in kid:
+                rows[kid[doc_key[u]]] = [kid[doc_key[c]] for c in g.col_idx[g.row_ptr[u]:g.row_ptr[u + 1]]]
+        row_ptr = np.zeros(n + 1, np.uint64)
+        row_ptr[1:] = np.cumsum([len(r) for r in rows])
+        col = np.array([c for r in rows for c in r], np.uint32)
+        cats = sorted(f"Top{c}" for c in range(5))
+        npg = [50000 + 12345 * int(c[3:]) for c in cats]
+        ref, _ = O.pagerank(row_ptr, col, 0.75, 1e-12, npg)
+        got = np.array([[f3[k][c] for c in cats] for k in keys])
+        assert np.abs(got - ref).sum(axis=0).max() <= 1e-9
+        # ---- ranking.UpdateTermWeights, title then body (start_crawl.go:176-177)
+        db.update_term_weights(engine, "title")
+        db.update_term_weights(engine, "body")
+        for t in ("inv0", "inv1", "forw4"):
+            db.save(t, tmp_path / f"{t}.w.jsonl")
+        f4 = host.read_jsonl(tmp_path / "forw4.w.jsonl")
+        total_docs = float(len(f3))
+        dense = {}
+        for name, tid, info in (("inv0", 0, "title"), ("inv1", 1, "body")):
+            t = tabs[name]
+            # doc ids of the synthetic table are node indices; re-key to the snapshot's dense ids
+            ow, omag = O.term_weights(t.term_ptr, t.doc_ids, t.norm_tf, len(doc_key), total_docs)
+            inv = host.read_jsonl(tmp_path / f"{name}.w.jsonl")
+            for term in (0, 3, 57):
+                a, b = int(t.term_ptr[term]), int(t.term_ptr[term + 1])
+                row = inv.get(md5(f"term{term}"), {})
+                assert len(row) == b - a
+                for p in range(a, b):
+                    assert np.float32(row[doc_key[t.doc_ids[p]]][0]) == ow[p]
+            for d in range(len(doc_key)):
+                if omag[d] > 0:
+                    assert f4[doc_key[d]][info] == omag[d]
+            dense[name] = (t, ow, omag)
+        # ---- retrieval.Retrieve: keyword + phrase queries on hashed tokens
+        tt, tw, tmag = dense["inv0"]
+        bt, bw, bmag = dense["inv1"]
+        ot = O.Table(tt.term_ptr, tt.doc_ids, tw, tt.pos_ptr, tt.pos)
+        ob = O.Table(bt.term_ptr, bt.doc_ids, bw, bt.pos_ptr, bt.pos)
+        for kw, ph in (([3, 17], []), ([0], [8, 9]), ([5, 5, 40], [16, 17, 18]), ([], [2]), ([9999], [])):
+            res = db.retrieve(engine, [md5(f"term{t}") for t in kw], [md5(f"term{t}") for t in ph])
+            ref = O.score_batch(ot, ob, len(doc_key), tmag, bmag, None, [0, len(kw)],
+                                [t if t < 120 else 0xFFFFFFFF for t in kw], [0, len(ph)], ph, k=50)
+            cnt = int(ref[3][0])
+            assert len(res) == cnt
+            # same docs in the same order up to ties: compare as (score desc, hash asc) since the snapshot's
+            # dense ids are ranks of the hashes, not the synthetic indices
+            exp = sorted(((ref[1][0][j], doc_key[ref[0][0][j]]) for j in range(cnt)), key=lambda x: (-x[0], x[1]))
+            if cnt < 50:  # complete result list: ordering by (score, hash) is fully determined
+                assert [r["DocHash"] for r in res] == [h for _, h in exp]
+            assert np.allclose([r["FinalRank"] for r in res], [s for s, _ in exp], rtol=1e-6, atol=0)
+            assert all(r["PageRank"] == 0.0 for r in res)  # topicProbs nil as shipped
+    finally:
+        db.close()
