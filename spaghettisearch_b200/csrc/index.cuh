@@ -41,6 +41,9 @@ struct IndexState {
   ss::DevBuf<float4> meta32;
   bool meta32_valid = false;
   int meta32_mode = -1;
+  // all weights finite and >= 0 (checked lazily by score.cu; enables the fp32 screened path)
+  bool wcheck_valid = false;
+  bool weights_nonneg = false;
   ss_score_stats stats{};
   // grow-only device workspace of ss_score_batch (cudaMalloc/cudaFree per batch would
   // synchronise the device and dominate small batches)
