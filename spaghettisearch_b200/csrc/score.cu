@@ -54,6 +54,8 @@ struct ScoreParams {
   TableView tab[2];      // 0 = title, 1 = body
   const double* mag[2];
   const float4* meta32;  // [D] {1/mag_title, 1/mag_body, blend bound, 0} in fp32 for the screening pass
+  int prefetch_meta;       // issue L1 prefetches of the screening records per sub-range
+  const uint32_t* narrow;  // [list][n_slabs+1] posting offset (from the term's row start) of every slab boundary
   uint32_t sort_max;     // slabs with at most this many postings take the sort path (<= kSortMax)
   int screen_ok;         // every weight is finite and >= 0: fp32 sums bound the exact ones (no cancellation)
   const double* sqd;     // [D] blend term for a shared topic vector, or NULL
@@ -499,14 +501,13 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
     const uint32_t tok = l >> 1, tb = l & 1;
     const uint32_t term = tok < n_kw ? p.kw_terms[kb + tok] : p.ph_terms[pb + (tok - n_kw)];
     const TableView& tv = p.tab[tb];
-    unsigned long long a = 0, b = 0;
-    if (tv.term_ptr && term < tv.V) {  // unknown term => empty row (main_retrieve.go:193,218)
-      a = tv.term_ptr[term];
-      b = tv.term_ptr[term + 1];
-    }
-    a = lower_bound_doc(tv.doc_ids, a, b, slab_lo);
-    s.base[l] = a;
-    s.len[l] = (uint32_t)(lower_bound_doc(tv.doc_ids, a, b, slab_hi) - a);
+    unsigned long long a = 0;
+    if (tv.term_ptr && term < tv.V) a = tv.term_ptr[term];  // unknown term => empty row (main_retrieve.go:193,218)
+    // slab boundaries of every list were located once for the whole batch (k_narrow)
+    const uint32_t* nar = p.narrow + ((size_t)2 * (kb + pb) + l) * (p.n_slabs + 1) + slab;
+    const uint32_t o0 = nar[0], o1 = nar[1];
+    s.base[l] = a + o0;
+    s.len[l] = o1 - o0;
   }
   __syncthreads();
 
@@ -526,6 +527,8 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
     for (uint32_t t = 0; t < p.T; ++t) blend_scale += fabsf((float)p.probs[(uint64_t)q * p.T + t]);
     blend_scale *= 1.0001f;
   }
+  // screening coefficients: 100 * (0.33 * blend, 0.38 / |q|, 0.29 / |q|)
+  const float sc_a = 33.0f * blend_scale, sc_t = 38.0f * qf_inv, sc_b = 29.0f * qf_inv;
   unsigned long long n_postings = 0, n_matched = 0;
 
   if (work == 0) {
@@ -631,6 +634,12 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
       continue;
     }
 
+    // the screening records of this sub-range (kRange x 16 B, one 128-byte line per thread) are
+    // requested now so that they arrive in L1 while the postings are being applied
+    if (p.prefetch_meta) {
+      const uint64_t first = d0 + (uint64_t)tid * 8;
+      if (first < p.D) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.meta32 + first));
+    }
     // keyword tokens in query order (duplicates count again); a barrier only after a token
     // that touched the accumulators
     bool any = false;
@@ -681,21 +690,32 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
         slot[r] = wi * 32 + lane;
       }
       if (any_word) {  // warp uniform: something matched in this warp's words
+        const float4* meta_base = p.meta32 + d0;
 #pragma unroll
         for (int r = 0; r < kWordsPerWarp; ++r) {
-          meta[r] = p.meta32[d0 + (has[r] ? slot[r] : 0u)];
+          meta[r] = meta_base[has[r] ? slot[r] : 0u];
           tr[r] = s.acc[0][slot[r]];
           br[r] = s.acc[1][slot[r]];
         }
+        // the running k-th best only changes in merge_candidates, i.e. between batches
+        const float thr_f = s.top_n >= k ? s.thr_f : -__int_as_float(0x7f800000);
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < kWordsPerWarp; ++r) {
-          if (lane == 0) s.bits[w0 + warp + r * (kT / 32)] = 0;
+          const uint32_t wi = w0 + warp + r * (kT / 32);
+          if (lane == 0) {
+            n_matched += __popc(s.bits[wi]);
+            s.bits[wi] = 0;
+          }
           if (!has[r]) continue;
           s.acc[0][slot[r]] = 0.0;
           s.acc[1][slot[r]] = 0.0;
-          ++n_matched;
-          finish_doc(p, s, q, d0 + slot[r], tr[r], br[r], meta[r], qf_inv, blend_scale, qm, k);
+          // screening (see finish_doc): sc_a/sc_t/sc_b fold the blend weights, 1/|q| and the x100
+          const float a = sc_a * meta[r].z;
+          const float b = tr[r] != 0.0 ? sc_t * ((float)tr[r] * meta[r].x) : 0.0f;
+          const float c = br[r] != 0.0 ? sc_b * ((float)br[r] * meta[r].y) : 0.0f;
+          if ((a + b + c) + (fabsf(a) + fabsf(b) + fabsf(c)) * 1e-4f + 1e-30f < thr_f) continue;
+          finish_exact(p, s, q, d0 + slot[r], tr[r], br[r], qm, k);
         }
       }
       if (kBatch < kRange) {  // the candidate buffer holds one batch: merge between batches
@@ -790,6 +810,37 @@ __global__ void __launch_bounds__(kT) k_merge(uint32_t n_lists, uint32_t k, uint
     }
   }
   if (threadIdx.x == 0) out_count[q] = min(total, k);
+}
+
+// Slab boundaries of every posting list of the batch: narrow[list][j] = offset, inside the
+// term's row, of the first posting with doc >= j * slab_docs.  One independent binary search
+// per (list, boundary) instead of a dependent chain at the start of every (query, slab) CTA.
+__global__ void k_narrow(ScoreParams p, uint32_t* __restrict__ narrow, uint64_t n_entries) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_entries) return;
+  const uint32_t per = p.n_slabs + 1;
+  const uint64_t list = i / per;
+  const uint32_t j = (uint32_t)(i % per);
+  // list -> (query, token, table): lists are laid out query by query, keyword tokens then phrase tokens
+  uint64_t lo = 0, hi = p.n_q;  // last q with 2*(kw_ptr[q] + ph_ptr[q]) <= list
+  while (hi - lo > 1) {
+    const uint64_t mid = (lo + hi) >> 1;
+    const uint64_t first = 2 * (p.kw_ptr[mid] + (p.ph_ptr ? p.ph_ptr[mid] : 0));
+    if (first <= list) lo = mid; else hi = mid;
+  }
+  const uint64_t q = lo;
+  const uint64_t kb = p.kw_ptr[q], n_kw = p.kw_ptr[q + 1] - kb, pb = p.ph_ptr ? p.ph_ptr[q] : 0;
+  const uint32_t l = (uint32_t)(list - 2 * (kb + pb));
+  const uint32_t tok = l >> 1, tb = l & 1;
+  const uint32_t term = tok < n_kw ? p.kw_terms[kb + tok] : p.ph_terms[pb + (tok - n_kw)];
+  const TableView& tv = p.tab[tb];
+  uint32_t off = 0;
+  if (tv.term_ptr && term < tv.V) {
+    const uint64_t a = tv.term_ptr[term], b = tv.term_ptr[term + 1];
+    const uint64_t target = min(p.D, (uint64_t)j * p.slab_docs);
+    off = (uint32_t)(lower_bound_doc(tv.doc_ids, a, b, j == p.n_slabs ? p.D : target) - a);
+  }
+  narrow[i] = off;
 }
 
 // sqd[d] = sum_t probs[t] * pr[d][t], ascending t, separately rounded (get_metadata.go:39-42)
@@ -921,6 +972,8 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   SS_TRY(ws_reserve(ws.out_pr, n_q * k));
   SS_TRY(ws_reserve(ws.out_count, n_q));
   SS_TRY(ws_reserve(ws.stats, 2));
+  const uint64_t n_narrow = 2 * (n_kw + n_ph) * (n_slabs + 1);
+  SS_TRY(ws_reserve(ws.narrow, n_narrow));
   // a table that was never loaded behaves as an empty one with zero norms
   if ((!ix->tab[0].loaded || !ix->tab[1].loaded) && ws.zero_mag.n < std::max<uint64_t>(D, 1)) {
     SS_TRY(ws.zero_mag.alloc(D));
@@ -1027,6 +1080,11 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   p.part_count = ws.part_count.p;
   p.stats = ws.stats.p;
 
+  p.narrow = ws.narrow.p;
+  p.prefetch_meta = 0;  // measured: no effect (the finalize step is issue bound, not latency bound)
+  if (const char* env = getenv("SS_SCORE_PREFETCH")) p.prefetch_meta = atoi(env);
+  if (n_narrow) k_narrow<<<ss::div_up(n_narrow, 256), 256, 0, st>>>(p, ws.narrow.p, n_narrow);
+  ++launches;
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[1], st));
   k_score<<<(unsigned)(n_q * n_slabs), kT, sizeof(Smem), st>>>(p);
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[2], st));
