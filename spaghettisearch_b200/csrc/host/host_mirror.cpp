@@ -2,7 +2,14 @@
 #include "host_mirror.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <future>
+#include <mutex>
+#include <thread>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -460,32 +467,122 @@ Index::Index(ss_engine* e, db::Table forw[6], db::Table inv[3]) : e_(e) {
   }
 }
 
-std::vector<Rank_combined> Index::Retrieve(const std::vector<std::string>& queryTokenised,
-                                           const std::vector<std::string>& phraseTokenised, uint32_t k) const {
-  auto ids = [&](const std::vector<std::string>& toks) {
-    std::vector<uint32_t> out;
+std::vector<std::vector<Rank_combined>> Index::RetrieveBatch(const std::vector<Query>& queries, uint32_t k) const {
+  auto ids = [&](const std::vector<std::string>& toks, std::vector<uint32_t>& out) {
     for (auto& t : toks) {
       auto it = term_id_.find(t);
       out.push_back(it == term_id_.end() ? 0xFFFFFFFFu : it->second);  // ErrKeyNotFound => empty row
     }
-    return out;
   };
-  std::vector<uint32_t> kw = ids(queryTokenised), ph = ids(phraseTokenised);
-  const uint64_t kw_ptr[2] = {0, kw.size()}, ph_ptr[2] = {0, ph.size()};
-  std::vector<uint32_t> docs(k);
-  std::vector<double> fin(k), pr(k);
-  uint32_t count = 0;
+  const size_t Q = queries.size();
+  std::vector<uint64_t> kw_ptr(Q + 1, 0), ph_ptr(Q + 1, 0);
+  std::vector<uint32_t> kw, ph;
+  for (size_t i = 0; i < Q; ++i) {
+    ids(queries[i].queryTokenised, kw);
+    ids(queries[i].phraseTokenised, ph);
+    kw_ptr[i + 1] = kw.size();
+    ph_ptr[i + 1] = ph.size();
+  }
+  std::vector<uint32_t> docs(Q * k), count(Q);
+  std::vector<double> fin(Q * k), pr(Q * k);
   // topicProbs is a nil map in the shipped code (main_retrieve.go:87-88) => NULL => sqd = 0
-  must(ss_score_batch(e_, 1, kw_ptr, ptr_or_null(kw), ph_ptr, ptr_or_null(ph), nullptr, 0, k, docs.data(), fin.data(),
-                      pr.data(), &count),
-       "ss_score_batch");
-  std::vector<Rank_combined> out(count);
-  for (uint32_t i = 0; i < count; ++i) {
-    out[i].DocHash = doc_keys_[docs[i]];
-    out[i].PageRank = pr[i];
-    out[i].FinalRank = fin[i];
+  if (Q)
+    must(ss_score_batch(e_, Q, kw_ptr.data(), ptr_or_null(kw), ph_ptr.data(), ptr_or_null(ph), nullptr, 0, k,
+                        docs.data(), fin.data(), pr.data(), count.data()),
+         "ss_score_batch");
+  std::vector<std::vector<Rank_combined>> out(Q);
+  for (size_t i = 0; i < Q; ++i) {
+    out[i].resize(count[i]);
+    for (uint32_t j = 0; j < count[i]; ++j) {
+      out[i][j].DocHash = doc_keys_[docs[i * k + j]];
+      out[i][j].PageRank = pr[i * k + j];
+      out[i][j].FinalRank = fin[i * k + j];
+    }
   }
   return out;
+}
+
+std::vector<Rank_combined> Index::Retrieve(const std::vector<std::string>& queryTokenised,
+                                           const std::vector<std::string>& phraseTokenised, uint32_t k) const {
+  return RetrieveBatch({Query{queryTokenised, phraseTokenised}}, k)[0];
+}
+
+struct BatchingRetriever::Impl {
+  struct Pending {
+    Index::Query q;
+    std::promise<std::vector<Rank_combined>> done;
+  };
+  const Index& index;
+  uint32_t k, max_batch, window_us;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<Pending> queue;
+  bool stop = false;
+  uint64_t n_batches = 0, n_queries = 0;
+  std::thread worker;
+  Impl(const Index& ix, uint32_t k_, uint32_t mb, uint32_t win) : index(ix), k(k_), max_batch(mb), window_us(win) {
+    worker = std::thread([this] { run(); });
+  }
+  void run() {
+    for (;;) {
+      std::vector<Pending> batch;
+      {
+        std::unique_lock<std::mutex> lock(mu);
+        cv.wait(lock, [&] { return stop || !queue.empty(); });
+        if (stop && queue.empty()) return;
+        // let the window fill: concurrent callers that arrive within it share one kernel launch
+        const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(window_us);
+        cv.wait_until(lock, deadline, [&] { return stop || queue.size() >= max_batch; });
+        while (!queue.empty() && batch.size() < max_batch) {
+          batch.push_back(std::move(queue.front()));
+          queue.pop_front();
+        }
+      }
+      std::vector<Index::Query> qs;
+      qs.reserve(batch.size());
+      for (auto& b : batch) qs.push_back(b.q);
+      try {
+        auto res = index.RetrieveBatch(qs, k);
+        for (size_t i = 0; i < batch.size(); ++i) batch[i].done.set_value(std::move(res[i]));
+      } catch (...) {
+        for (auto& b : batch) b.done.set_exception(std::current_exception());
+      }
+      std::lock_guard<std::mutex> lock(mu);
+      ++n_batches;
+      n_queries += batch.size();
+    }
+  }
+};
+
+BatchingRetriever::BatchingRetriever(const Index& index, uint32_t k, uint32_t max_batch, uint32_t window_us)
+    : impl_(new Impl(index, k, std::max(1u, max_batch), window_us)) {}
+BatchingRetriever::~BatchingRetriever() {
+  {
+    std::lock_guard<std::mutex> lock(impl_->mu);
+    impl_->stop = true;
+  }
+  impl_->cv.notify_all();
+  impl_->worker.join();
+  delete impl_;
+}
+std::vector<Rank_combined> BatchingRetriever::Submit(const std::vector<std::string>& queryTokenised,
+                                                     const std::vector<std::string>& phraseTokenised) {
+  std::future<std::vector<Rank_combined>> fut;
+  {
+    std::lock_guard<std::mutex> lock(impl_->mu);
+    impl_->queue.push_back({Index::Query{queryTokenised, phraseTokenised}, {}});
+    fut = impl_->queue.back().done.get_future();
+  }
+  impl_->cv.notify_all();
+  return fut.get();  // rethrows the worker's exception: the reference panics
+}
+uint64_t BatchingRetriever::batches() const {
+  std::lock_guard<std::mutex> lock(impl_->mu);
+  return impl_->n_batches;
+}
+uint64_t BatchingRetriever::queries() const {
+  std::lock_guard<std::mutex> lock(impl_->mu);
+  return impl_->n_queries;
 }
 
 std::vector<Rank_combined> Retrieve(ss_engine* e, const std::vector<std::string>& queryTokenised,
@@ -561,6 +658,62 @@ SSH_API int ssh_update_term_weights(void* d, void* engine, const char* info) {
   return guarded([&] {
     db::DB* x = (db::DB*)d;
     ranking::UpdateTermWeights((ss_engine*)engine, std::string(info) == "title" ? &x->inv[0] : &x->inv[1], x->forw, info);
+  });
+}
+// Serve `n` queries (newline separated; keyword hashes, then '|' and phrase hashes) from `threads`
+// concurrent callers through a BatchingRetriever; out = one JSON array per line in query order.
+// stats[0] = ss_score_batch calls made, stats[1] = queries served.
+SSH_API int ssh_retrieve_concurrent(void* d, void* engine, const char* queries, int threads, int window_us,
+                                    char* out, size_t cap, unsigned long long* stats) {
+  return guarded([&] {
+    db::DB* x = (db::DB*)d;
+    std::vector<std::pair<std::vector<std::string>, std::vector<std::string>>> qs;
+    std::istringstream in(queries ? queries : "");
+    std::string line;
+    while (std::getline(in, line)) {
+      const size_t bar = line.find('|');
+      qs.emplace_back(split(line.substr(0, bar).c_str()),
+                      bar == std::string::npos ? std::vector<std::string>() : split(line.substr(bar + 1).c_str()));
+    }
+    retrieval::Index index((ss_engine*)engine, x->forw, x->inv);
+    std::vector<std::vector<retrieval::Rank_combined>> res(qs.size());
+    {
+      retrieval::BatchingRetriever batcher(index, 50, 4096, (uint32_t)window_us);
+      std::vector<std::thread> pool;
+      std::atomic<size_t> next{0};
+      std::string err;
+      std::mutex err_mu;
+      for (int t = 0; t < std::max(1, threads); ++t)
+        pool.emplace_back([&] {
+          for (size_t i = next++; i < qs.size(); i = next++) {
+            try {
+              res[i] = batcher.Submit(qs[i].first, qs[i].second);
+            } catch (const std::exception& ex) {
+              std::lock_guard<std::mutex> lock(err_mu);
+              err = ex.what();
+            }
+          }
+        });
+      for (auto& th : pool) th.join();
+      if (stats) {
+        stats[0] = batcher.batches();
+        stats[1] = batcher.queries();
+      }
+      if (!err.empty()) fail(err);
+    }
+    std::string js;
+    for (auto& r : res) {
+      js += "[";
+      for (size_t i = 0; i < r.size(); ++i) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "%s{\"DocHash\": \"%s\", \"PageRank\": %.17g, \"FinalRank\": %.17g}", i ? ", " : "",
+                 r[i].DocHash.c_str(), r[i].PageRank, r[i].FinalRank);
+        js += buf;
+      }
+      js += "]\n";
+    }
+    if (js.size() + 1 > cap) fail("result buffer too small");
+    memcpy(out, js.c_str(), js.size() + 1);
   });
 }
 // results as JSON: [{"DocHash": "...", "PageRank": x, "FinalRank": y}, ...] into out (NUL terminated)

@@ -89,11 +89,35 @@ class Index {
   // tokens are md5-hex hashes of the laundered words (main_retrieve.go:28-36); duplicates kept
   std::vector<Rank_combined> Retrieve(const std::vector<std::string>& queryTokenised,
                                       const std::vector<std::string>& phraseTokenised, uint32_t k = 50) const;
+  // a whole batch in one ss_score_batch call; results[i] belongs to queries[i]
+  struct Query {
+    std::vector<std::string> queryTokenised, phraseTokenised;
+  };
+  std::vector<std::vector<Rank_combined>> RetrieveBatch(const std::vector<Query>& queries, uint32_t k = 50) const;
 
  private:
   ss_engine* e_;
   std::vector<std::string> doc_keys_;
   std::map<std::string, uint32_t> term_id_;
+};
+
+// Query front-end batching: retrieval.Retrieve is called concurrently, one
+// goroutine per HTTP request (cmd/server/server.go:32-52), but the scoring kernel wants batches.
+// Submit() may be called from any number of threads; a worker collects what arrived within
+// `window_us` (or `max_batch` queries), scores them in one ss_score_batch call and hands each
+// caller its own result.  Same results as Index::Retrieve, query by query.
+class BatchingRetriever {
+ public:
+  BatchingRetriever(const Index& index, uint32_t k = 50, uint32_t max_batch = 4096, uint32_t window_us = 200);
+  ~BatchingRetriever();
+  std::vector<Rank_combined> Submit(const std::vector<std::string>& queryTokenised,
+                                    const std::vector<std::string>& phraseTokenised);
+  uint64_t batches() const;   // ss_score_batch calls so far
+  uint64_t queries() const;   // queries served so far
+
+ private:
+  struct Impl;
+  Impl* impl_;
 };
 
 std::vector<Rank_combined> Retrieve(ss_engine* e, const std::vector<std::string>& queryTokenised,

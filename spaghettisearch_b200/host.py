@@ -34,6 +34,8 @@ def lib():
         L.ssh_update_pagerank.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double]
         L.ssh_update_term_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
         L.ssh_retrieve.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
+        L.ssh_retrieve_concurrent.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p,
+                                              C.c_size_t, C.POINTER(C.c_ulonglong)]
         _lib = L
     return _lib
 
@@ -78,6 +80,20 @@ class DB:
         self._ok(self.L.ssh_retrieve(self.h, engine.h, " ".join(kw_hashes).encode(), " ".join(ph_hashes).encode(), buf,
                                      len(buf)))
         return json.loads(buf.value.decode())
+
+
+def _retrieve_concurrent(self, engine, queries, threads=8, window_us=200):
+    """queries: list of (kw_hashes, ph_hashes); served through the C++ BatchingRetriever from `threads`
+    concurrent callers -> (results per query, ss_score_batch calls made)."""
+    text = "\n".join(" ".join(kw) + "|" + " ".join(ph) for kw, ph in queries)
+    buf = C.create_string_buffer(1 << 24)
+    stats = (C.c_ulonglong * 2)()
+    self._ok(self.L.ssh_retrieve_concurrent(self.h, engine.h, text.encode(), threads, window_us, buf, len(buf), stats))
+    lines = buf.value.decode().splitlines()
+    return [json.loads(l) for l in lines], int(stats[0]), int(stats[1])
+
+
+DB.retrieve_concurrent = _retrieve_concurrent
 
 
 def write_jsonl(path, rows):

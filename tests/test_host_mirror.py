@@ -175,5 +175,17 @@ def test_go_api_over_snapshots(engine, tmp_path):
                 assert [r["DocHash"] for r in res] == [h for _, h in exp]
             assert np.allclose([r["FinalRank"] for r in res], [s for s, _ in exp], rtol=1e-6, atol=0)
             assert all(r["PageRank"] == 0.0 for r in res)  # topicProbs nil as shipped
+        # ---- query front-end batching: concurrent callers, one kernel launch per window,
+        # every caller gets exactly what a lone Retrieve returns
+        rng = np.random.default_rng(1)
+        qs = []
+        for i in range(200):
+            kw = [md5(f"term{int(t)}") for t in rng.integers(0, 120, int(rng.integers(1, 4)))]
+            ph = [md5(f"term{int(t)}") for t in rng.integers(0, 119, 2)] if i % 5 == 0 else []
+            qs.append((kw, ph))
+        batched, n_calls, n_served = db.retrieve_concurrent(engine, qs, threads=16, window_us=2000)
+        assert n_served == len(qs) and n_calls < len(qs) / 2  # requests really were coalesced
+        for i in (0, 5, 17, 99, 199):
+            assert batched[i] == db.retrieve(engine, qs[i][0], qs[i][1])
     finally:
         db.close()
