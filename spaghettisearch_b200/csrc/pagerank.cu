@@ -66,6 +66,8 @@ struct SweepParams {
   const uint64_t* in_ptr;   // [rows_loc + 1], offsets into in_src
   const uint32_t* in_src;   // sources ascending within a row
   const double* mul;        // [rows_loc] d/out, or 0 for dangling rows
+  const uint32_t* in_ptr32; // in_ptr as 32-bit offsets, padded with E_loc (fast short-row kernel), or NULL
+  const double2* mul2;      // [rows_loc] {scale m (1 for dangling rows), 1/m (-1 for dangling rows)}
   const double* inv_tot;    // [TP] 1 / (S_t + (1-d) N)
   const double* init;       // [TP] 1/num_pages[t]
   double* red;              // [slots][3*TP] per-CTA partial sums (delta, S, changed)
@@ -307,6 +309,136 @@ __global__ void __launch_bounds__(kThreads, 4) k_sweep_short(SweepParams p, uint
   block_reduce<LPR, VEC>(p, acc, true);
 }
 
+// ---- short rows, lean variant ---------------------------------------------------
+// Same arithmetic, bit for bit, as k_sweep_short (same gather order, same epilogue
+// expressions), restructured after the round-1 ncu source profile: the first version
+// spent 72 % of its instructions outside the gathers and spilled its prefetched row
+// pointers, which serialised three memory round trips per row block.  Here
+//   * row pointers are 32-bit (local edge count < 2^32) and the array is padded, so the
+//     two-block-ahead pointer prefetch needs no bounds checks and two registers;
+//   * the row scale and its reciprocal come from one packed 16-byte record (no fp64
+//     divide per row), the per-topic 1/Tot is loaded once per kernel;
+//   * "first sweep" and "some topic frozen" are template parameters, the changed-bits
+//     test is an integer OR, shuffles run under the full mask with a warp-uniform trip
+//     count (no MATCH/BRA.DIV), and absent edges are predicated off instead of loading
+//     row 0.
+template <int VEC>
+struct Acc2 {
+  double d[VEC], s[VEC];
+  uint32_t chg;  // bit j: some row changed topic column j of this lane
+  __device__ Acc2() : chg(0) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) d[j] = s[j] = 0.0;
+  }
+};
+
+template <int LPR, int VEC, bool FIRST, bool ALL>
+__device__ __forceinline__ void epilogue2(const SweepParams& p, uint32_t r, int l8, Vec<VEC> a, const Vec<VEC>& yl,
+                                          double2 m2, const Vec<VEC>& inv_tot, const Vec<VEC>& init,
+                                          Acc2<VEC>& acc) {
+  constexpr int TP = LPR * VEC;
+  const uint64_t v = p.row_lo + r;
+  const bool has_out = m2.y > 0.0;
+  const double mul = m2.x, inv_mul = fabs(m2.y);
+  Vec<VEC> yn;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    double last_rank = yl.v[j] * inv_mul;
+    if (FIRST) {
+      a.v[j] += init.v[j];
+      last_rank = init.v[j];
+    }
+    const double nr = (a.v[j] + p.tele) * inv_tot.v[j];
+    const double cand = nr * mul;
+    const bool live = ALL || ((p.active_mask >> (VEC * l8 + j)) & 1u);
+    if (live) {
+      acc.d[j] += fabs(nr - last_rank);
+      yn.v[j] = cand;
+      acc.chg |= (__double_as_longlong(cand) != __double_as_longlong(yl.v[j])) ? (1u << j) : 0u;
+    } else {
+      yn.v[j] = yl.v[j];
+    }
+    acc.s[j] += has_out ? yn.v[j] : 0.0;
+  }
+  st_row_stream<VEC>(p.y_next + v * TP + VEC * l8, yn);
+  for (int q = 0; q < p.n_peers; ++q) st_row_plain<VEC>(p.peer_next[q] + v * TP + VEC * l8, yn);
+}
+
+template <int LPR, int VEC>
+__device__ __forceinline__ void block_reduce2(const SweepParams& p, const Acc2<VEC>& a2) {
+  Acc<VEC> acc;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    acc.d[j] = a2.d[j];
+    acc.s[j] = a2.s[j];
+    acc.c[j] = ((a2.chg >> j) & 1u) ? 1.0 : 0.0;
+  }
+  block_reduce<LPR, VEC>(p, acc, true);
+}
+
+template <int LPR, int VEC, bool FIRST, bool ALL>
+__global__ void __launch_bounds__(kThreads, 4) k_sweep_short32(SweepParams p, uint32_t n_row_blocks) {
+  constexpr int TP = LPR * VEC, GPW = 32 / LPR, GPC = GPW * (kThreads / 32);
+  const int lane = threadIdx.x & 31, l8 = lane % LPR, gbase = lane - l8;
+  const uint32_t group_in_cta = (threadIdx.x >> 5) * GPW + (lane / LPR);
+  const uint32_t* __restrict__ ptr = p.in_ptr32;
+  const uint32_t* __restrict__ src = p.in_src;
+  const double* __restrict__ y = p.y_last;
+  Acc2<VEC> acc;
+  const Vec<VEC> inv_tot = ld_row_plain<VEC>(p.inv_tot + VEC * l8);
+  Vec<VEC> init;
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) init.v[c] = FIRST ? p.init[VEC * l8 + c] : 0.0;
+  const uint32_t step = gridDim.x * GPC;
+  uint32_t r = blockIdx.x * GPC + group_in_cta;
+  // the pointer array is padded past rows_loc by three grid strides (ss_graph_load_csr)
+  uint32_t b_c = ptr[r], e_c = ptr[r + 1];
+  uint32_t b_n = ptr[r + step], e_n = ptr[r + step + 1];
+  uint32_t idx_c = (e_c - b_c <= kShortMax && b_c + l8 < e_c) ? __ldg(src + b_c + l8) : 0u;
+  for (uint32_t rb = blockIdx.x; rb < n_row_blocks; rb += gridDim.x, r += step) {
+    const uint32_t b = b_c, e = e_c;
+    uint32_t idx = idx_c;
+    b_c = b_n;
+    e_c = e_n;
+    b_n = ptr[r + 2 * step];
+    e_n = ptr[r + 2 * step + 1];
+    idx_c = (e_c - b_c <= kShortMax && b_c + l8 < e_c) ? __ldg(src + b_c + l8) : 0u;
+    const bool mine = r < p.rows_loc && e - b <= kShortMax;  // long rows: k_sweep_long / k_sweep_fix
+    const uint32_t deg = mine ? e - b : 0u;
+    Vec<VEC> yl;
+    double2 m2 = make_double2(1.0, -1.0);
+    if (mine) {
+      yl = ld_row_stream<VEC>(y + (p.row_lo + r) * TP + VEC * l8);
+      m2 = __ldg(p.mul2 + r);
+    }
+    Vec<VEC> a;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) a.v[c] = 0.0;
+    const uint32_t max_deg = __reduce_max_sync(0xFFFFFFFFu, deg);
+    for (uint32_t i = 0; i < max_deg; i += LPR) {
+      if (i) idx = (b + i + l8 < e) ? __ldg(src + b + i + l8) : 0u;
+      Vec<VEC> rows[LPR];
+#pragma unroll
+      for (int j = 0; j < LPR; ++j) {
+        const uint32_t u = __shfl_sync(0xFFFFFFFFu, idx, gbase + j);
+        if (i + j < deg) {
+          rows[j] = ld_row_gather<VEC>(y + (uint64_t)u * TP + VEC * l8);
+        } else {
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) rows[j].v[c] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < LPR; ++j)
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) a.v[c] += rows[j].v[c];
+    }
+    if (mine) epilogue2<LPR, VEC, FIRST, ALL>(p, r, l8, a, yl, m2, inv_tot, init, acc);
+  }
+  if (p.n_peers) __threadfence_system();
+  block_reduce2<LPR, VEC>(p, acc);
+}
+
 // Long-row tasks: one warp per task, 32 edges per step, group g takes edges
 // j*GPW+g; the GPW partial rows are combined with shuffles.  The next step's
 // indices are fetched before this step's rows.
@@ -460,7 +592,7 @@ template <int LPR, int VEC>
 __global__ void __launch_bounds__(kThreads) k_init(double* __restrict__ y, const uint32_t* __restrict__ outdeg,
                                                   uint64_t n_nodes, double damping, const double* __restrict__ init,
                                                   uint64_t row_lo, uint32_t rows_loc, double* __restrict__ mul_loc,
-                                                  double* __restrict__ red) {
+                                                  double2* __restrict__ mul2_loc, double* __restrict__ red) {
   constexpr int TP = LPR * VEC;
   __shared__ double sm[kThreads / 32][16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l8 = lane % LPR;
@@ -476,7 +608,11 @@ __global__ void __launch_bounds__(kThreads) k_init(double* __restrict__ y, const
     for (int c = 0; c < VEC; ++c) val.v[c] = m * init[VEC * l8 + c];
     st_row_plain<VEC>(y + v * TP + VEC * l8, val);
     if (v >= row_lo && v < row_lo + rows_loc) {
-      if (l8 == 0) mul_loc[v - row_lo] = od ? m : 0.0;
+      if (l8 == 0) {
+        mul_loc[v - row_lo] = od ? m : 0.0;
+        const bool has_out = od && m > 0.0;  // the sweeps' test (mul > 0)
+        mul2_loc[v - row_lo] = has_out ? make_double2(m, 1.0 / m) : make_double2(1.0, -1.0);
+      }
       if (od) {
 #pragma unroll
         for (int c = 0; c < VEC; ++c) s[c] += val.v[c];
@@ -580,6 +716,13 @@ __global__ void k_local_ptr(const unsigned long long* __restrict__ in_ptr_full, 
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r <= rows_loc) in_ptr_loc[r] = in_ptr_full[row_lo + r] - in_ptr_full[row_lo];
 }
+// 32-bit copy of the local row pointers, padded with E_loc (rows of degree 0) so that the lean
+// short-row kernel can prefetch pointers two grid strides ahead without bounds checks
+__global__ void k_local_ptr32(const uint64_t* __restrict__ in_ptr_loc, uint32_t rows_loc, uint64_t n_padded,
+                              uint32_t* __restrict__ out) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_padded) out[r] = (uint32_t)in_ptr_loc[r <= rows_loc ? r : rows_loc];
+}
 __global__ void k_count_tasks(const uint64_t* __restrict__ in_ptr, uint32_t rows_loc, uint32_t* __restrict__ nt,
                               uint32_t* __restrict__ nf) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -636,6 +779,9 @@ struct PagerankState {
   std::vector<uint64_t> bounds;  // [world + 1]
   ss::DevBuf<uint32_t> outdeg;   // [N]
   ss::DevBuf<uint64_t> in_ptr;   // [rows_loc + 1]
+  ss::DevBuf<uint32_t> in_ptr32; // [rows_loc + 1 + ptr32_pad], only when E_loc < 2^32
+  uint64_t ptr32_pad = 0;        // 0: no 32-bit copy
+  ss::DevBuf<double2> mul2;      // [rows_loc] {m, 1/m} or {1, -1}
   ss::DevBuf<uint32_t> in_src;   // [E_loc]
   ss::DevBuf<LongTask> tasks;
   ss::DevBuf<FixRow> fix;
@@ -866,6 +1012,16 @@ SS_API int ss_graph_load_csr(ss_engine* e, uint64_t n_nodes, uint64_t n_edges, c
   k_local_ptr<<<ss::div_up((uint64_t)s->rows_loc + 1, 256), 256, 0, st>>>(sc.in_ptr_full.p, s->row_lo, s->rows_loc,
                                                                          s->in_ptr.p);
 
+  s->ptr32_pad = 0;
+  if (s->E_loc < 0xFFFFFFFFull) {
+    // padding: GPC <= 256 rows per CTA and step, persistent grid <= 8 CTAs per SM, two strides ahead
+    const uint64_t pad = 2ull * (uint64_t)e->sm_count * 8 * 256 + 1024;
+    const uint64_t n_padded = (uint64_t)s->rows_loc + 1 + pad;
+    SS_TRY(s->in_ptr32.reserve(n_padded));
+    k_local_ptr32<<<ss::div_up(n_padded, 256), 256, 0, st>>>(s->in_ptr.p, s->rows_loc, n_padded, s->in_ptr32.p);
+    s->ptr32_pad = pad;
+  }
+
   // long-row tasks and fix rows
   s->n_tasks = s->n_fix = 0;
   if (s->rows_loc) {
@@ -956,14 +1112,23 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
 
   const int GPC = (32 / LPR) * (kThreads / 32);
   const uint32_t n_row_blocks = ss::div_up(R, GPC);
-  int occ_short = 4, occ_long = 4;
+  int occ_short = 4, occ_long = 4, occ_short32 = 4;
   dispatch_shape(shape, [&](auto lpr, auto vec) {
     constexpr int L = decltype(lpr)::value, V = decltype(vec)::value;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_short, k_sweep_short<L, V>, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_short32, k_sweep_short32<L, V, false, true>, kThreads, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_long, k_sweep_long<L, V>, kThreads, 0);
     return SS_OK;
   });
   // persistent grids: exactly one resident wave, static block-cyclic work split
+  // lean short-row kernel: needs the 32-bit pointer copy and its padding to cover two grid strides
+  const char* short_env = getenv("SS_PR_SHORT");
+  bool lean = s->ptr32_pad > 0 && !(short_env && !strcmp(short_env, "legacy"));
+  if (lean) {
+    const uint64_t need = 2ull * (uint64_t)e->sm_count * std::max(1, occ_short32) * GPC + GPC + 2;
+    if (need > s->ptr32_pad) lean = false;
+  }
+  if (lean) occ_short = occ_short32;
   const uint32_t grid_short =
       std::max(1u, std::min<uint32_t>(n_row_blocks, (uint32_t)(e->sm_count * std::max(1, occ_short))));
   const uint32_t grid_long = std::max(
@@ -983,6 +1148,7 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
     SS_TRY(s->y[1].reserve(N * TP));
   }
   SS_TRY(s->mul.reserve(R));
+  SS_TRY(s->mul2.reserve(R));
   SS_TRY(s->partials.reserve((size_t)s->n_tasks * TP));
   SS_TRY(s->red.reserve((size_t)red_slots * W));
   SS_TRY(s->sums.reserve(W));
@@ -1005,7 +1171,7 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
   int rc = dispatch_shape(shape, [&](auto lpr, auto vec) {
     constexpr int L = decltype(lpr)::value, V = decltype(vec)::value;
     k_init<L, V><<<grid_init, kThreads, 0, st>>>(s->y[0].p, s->outdeg.p, N, damping, s->init.p, s->row_lo, R, s->mul.p,
-                                             s->red.p);
+                                             s->mul2.p, s->red.p);
     return SS_OK;
   });
   SS_TRY(rc);
@@ -1016,7 +1182,8 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
   s->stats.launches += 4;
   s->cur = 0;
 
-  uint32_t active = T >= 32 ? 0xFFFFFFFFu : ((1u << T) - 1u);
+  const uint32_t all_topics = T >= 32 ? 0xFFFFFFFFu : ((1u << T) - 1u);
+  uint32_t active = all_topics;
   std::vector<uint32_t> iters(T, 0);
   std::vector<double> h_sums(W);
   bool hit_max = false;
@@ -1027,6 +1194,8 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
     p.in_ptr = s->in_ptr.p;
     p.in_src = s->in_src.p;
     p.mul = s->mul.p;
+    p.in_ptr32 = s->in_ptr32.p;
+    p.mul2 = s->mul2.p;
     p.inv_tot = s->tot.p;
     p.init = s->init.p;
     p.row_lo = s->row_lo;
@@ -1041,7 +1210,18 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
       constexpr int L = decltype(lpr)::value, V = decltype(vec)::value;
       SweepParams q = p;
       q.red = s->red.p;
-      k_sweep_short<L, V><<<grid_short, kThreads, 0, st>>>(q, n_row_blocks);
+      if (lean) {
+        const bool all = active == all_topics && T == TP;  // padded columns stay frozen through the mask
+        if (p.first) {
+          if (all) k_sweep_short32<L, V, true, true><<<grid_short, kThreads, 0, st>>>(q, n_row_blocks);
+          else k_sweep_short32<L, V, true, false><<<grid_short, kThreads, 0, st>>>(q, n_row_blocks);
+        } else {
+          if (all) k_sweep_short32<L, V, false, true><<<grid_short, kThreads, 0, st>>>(q, n_row_blocks);
+          else k_sweep_short32<L, V, false, false><<<grid_short, kThreads, 0, st>>>(q, n_row_blocks);
+        }
+      } else {
+        k_sweep_short<L, V><<<grid_short, kThreads, 0, st>>>(q, n_row_blocks);
+      }
       q.red = s->red.p + (size_t)grid_short * W;
       k_sweep_long<L, V><<<grid_long, kThreads, 0, st>>>(q, s->tasks.p, s->n_tasks, s->partials.p);
       if (timing) cudaEventRecord(s->ev[1], st);

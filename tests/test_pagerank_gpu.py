@@ -53,6 +53,21 @@ def test_random_graphs(engine, n, e, seed):
     assert np.isfinite(got).all() and (got > 0).all()
 
 
+def test_lean_short_row_kernel_matches_legacy_bitwise(engine, monkeypatch):
+    # k_sweep_short32 (32-bit padded row pointers, packed scale record) must reproduce the first
+    # short-row kernel bit for bit: same gather order, same epilogue expressions.  Frozen topics
+    # (different num_pages -> different sweep counts) exercise the masked instantiations.
+    g = synth.graph(60000, 900000, seed=13)
+    engine.graph_load_csr(g.row_ptr, g.col_idx)
+    for npg, eps in ((synth.topics(16), 1e-9), ([3, 50000, 7, 1000000, 11], 1e-13)):
+        monkeypatch.setenv("SS_PR_SHORT", "legacy")
+        a, ia, _ = engine.pagerank(0.75, eps, npg)
+        monkeypatch.delenv("SS_PR_SHORT")
+        b, ib, _ = engine.pagerank(0.75, eps, npg)
+        assert ia.tolist() == ib.tolist()
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
 def test_damping_085_and_tight_eps(engine):
     g = synth.graph(20000, 300000, seed=5)
     _check(engine, g.row_ptr, g.col_idx, 0.85, 1e-12, synth.topics(16))
