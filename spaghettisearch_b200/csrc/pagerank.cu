@@ -41,7 +41,7 @@ namespace {
 #ifndef SS_GATHER_EVICT_LAST
 #define SS_GATHER_EVICT_LAST 0
 #endif
-constexpr uint32_t kShortMax = 32;   // longest row handled by one sub-warp
+constexpr uint32_t kShortMax = 16;   // longest row handled by one sub-warp (the async ring holds 32/LPR such rows + 31)
 constexpr uint32_t kChunk = 512;     // edges per long-row task
 constexpr int kThreads = 256;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
@@ -67,7 +67,10 @@ struct SweepParams {
   const uint32_t* in_src;   // sources ascending within a row
   const double* mul;        // [rows_loc] d/out, or 0 for dangling rows
   const uint32_t* in_ptr32; // in_ptr as 32-bit offsets, padded with E_loc (fast short-row kernel), or NULL
-  const double2* mul2;      // [rows_loc] {scale m (1 for dangling rows), 1/m (-1 for dangling rows)}
+  const double2* mul2;      // [rows_loc] {scale m (1 for dangling rows; 0 marks a long row), 1/m (-1: dangling)}
+  const uint32_t* sptr;     // [rows_loc + 1 (+pad)] row pointers into ssrc: short rows only, long rows are empty
+  const uint32_t* ssrc;     // sources of the short rows, compacted in row order
+  const uint32_t* warp_rows;  // [n_warps + 1] row range of every warp of the async short-row kernel
   const double* inv_tot;    // [TP] 1 / (S_t + (1-d) N)
   const double* init;       // [TP] 1/num_pages[t]
   double* red;              // [slots][3*TP] per-CTA partial sums (delta, S, changed)
@@ -439,6 +442,174 @@ __global__ void __launch_bounds__(kThreads, 4) k_sweep_short32(SweepParams p, ui
   block_reduce2<LPR, VEC>(p, acc);
 }
 
+// ---- short rows, asynchronous gather ring -----------------------------------------
+// The lean kernel above is bound by how many row loads fit in registers: 8 x 16 B per lane,
+// half of them empty for the average short row, against a loaded memory latency of ~2.5 us
+// (ncu: 79 % long-scoreboard stalls at 35 % DRAM utilisation).  Here the gathered rows land in
+// shared memory instead (cp.async, 16 B per lane, LPR lanes per row): every warp owns a ring
+// of kRingBytes / (TP * 8) row slots, streams the compacted short-row source list `ssrc` in
+// 32-edge windows, and keeps up to four windows (128 rows at T = 16) in flight, all of them
+// real edges.  The consumer half of the same warp walks its rows in order, one row per LPR-lane
+// group, adds the landed rows in ascending source order (the same sums, bit for bit, as the
+// register kernels) and runs the fused epilogue.  Each warp owns one contiguous row range
+// (edge- and row-balanced, k_short_partition), so the pipeline never drains inside a sweep.
+constexpr int kAsyncThreads = 128;
+constexpr int kRingBytes = 16384;  // per warp
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int LPR, int NT>
+__device__ __forceinline__ void block_reduce_nt(const SweepParams& p, const Acc2<2>& acc) {
+  constexpr int TP = LPR * 2, kWarps = NT / 32;
+  __shared__ double sm[kWarps][3 * 16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l8 = lane % LPR;
+  double v[6];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    v[j] = acc.d[j];
+    v[2 + j] = acc.s[j];
+    v[4 + j] = ((acc.chg >> j) & 1u) ? 1.0 : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) v[i] += __shfl_xor_sync(0xFFFFFFFFu, v[i], o);
+  if (lane < LPR) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      sm[warp][2 * l8 + j] = v[j];
+      sm[warp][TP + 2 * l8 + j] = v[2 + j];
+      sm[warp][2 * TP + 2 * l8 + j] = v[4 + j];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 * TP) {
+    double t = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) t += sm[w][threadIdx.x];
+    p.red[(size_t)blockIdx.x * 3 * TP + threadIdx.x] = t;
+  }
+}
+
+template <int LPR, bool FIRST, bool ALL>
+__global__ void __launch_bounds__(kAsyncThreads, 3) k_sweep_short_async(SweepParams p) {
+  constexpr int VEC = 2, TP = LPR * VEC, GPW = 32 / LPR, ROWB = TP * 8;
+  constexpr uint32_t S = kRingBytes / ROWB;  // ring slots: >= GPW * kShortMax + 32, power of two
+  static_assert(S >= GPW * kShortMax + 32 && (S & (S - 1)) == 0, "ring too small");
+  constexpr uint32_t kMaxAhead = S / 32;     // windows that fit in the ring
+  extern __shared__ __align__(128) unsigned char ring_raw[];
+  const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5, l8 = lane % LPR, g = lane / LPR;
+  const uint32_t gw = blockIdx.x * (kAsyncThreads / 32) + warp_in_cta;
+  unsigned char* ring = ring_raw + (size_t)warp_in_cta * kRingBytes;
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+  const uint32_t* __restrict__ sptr = p.sptr;
+  const uint32_t* __restrict__ ssrc = p.ssrc;
+  const double* __restrict__ y = p.y_last;
+  const uint32_t r_lo = p.warp_rows[gw], r_hi = p.warp_rows[gw + 1];
+  const uint32_t e_lo = sptr[r_lo], e_hi = sptr[r_hi];
+  Acc2<VEC> acc;
+  const Vec<VEC> inv_tot = ld_row_plain<VEC>(p.inv_tot + VEC * l8);
+  Vec<VEC> init;
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) init.v[c] = FIRST ? p.init[VEC * l8 + c] : 0.0;
+
+  // producer state: windows are absolute 32-edge blocks of ssrc; pw = next window to issue
+  uint32_t pw = e_lo >> 5;
+  const uint32_t w_end = (e_hi + 31) >> 5;  // one past the last window holding an edge of this warp
+  auto load_idx = [&](uint32_t w) -> uint32_t {
+    const uint32_t j = w * 32 + lane;
+    return (w < w_end && j >= e_lo && j < e_hi) ? __ldg(ssrc + j) : kNone;
+  };
+  uint32_t idx_next = load_idx(pw);
+  auto issue_window = [&]() {
+    const uint32_t idx = idx_next;
+    idx_next = load_idx(pw + 1);
+    const uint32_t slot0 = (pw * 32) & (S - 1);
+#pragma unroll
+    for (int k = 0; k < LPR; ++k) {
+      const int t = k * GPW + g;  // edge of the window handled by this lane group in step k
+      const uint32_t u = __shfl_sync(0xFFFFFFFFu, idx, t);
+      if (u != kNone) cp_async16(ring_s + (slot0 + t) * ROWB + l8 * 16, y + (uint64_t)u * TP + VEC * l8);
+    }
+    cp_async_commit();
+    ++pw;
+  };
+  // fill the ring
+  for (uint32_t k = 0; k < kMaxAhead && pw < w_end; ++k) issue_window();
+
+  uint32_t r = r_lo + g;
+  uint32_t b_n = 0, e_n = 0;
+  Vec<VEC> yl_n;
+  double2 m2_n = make_double2(0.0, -1.0);
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) yl_n.v[c] = 0.0;
+  auto prefetch_row = [&](uint32_t rr) {
+    b_n = e_n = e_hi;
+    m2_n = make_double2(0.0, -1.0);
+    if (rr < r_hi) {
+      b_n = sptr[rr];
+      e_n = sptr[rr + 1];
+      m2_n = __ldg(p.mul2 + rr);
+      yl_n = ld_row_stream<VEC>(y + (p.row_lo + rr) * TP + VEC * l8);
+    }
+  };
+  prefetch_row(r);
+  for (uint32_t r0 = r_lo; r0 < r_hi; r0 += GPW, r += GPW) {
+    const uint32_t b = b_n, e = e_n;
+    const Vec<VEC> yl = yl_n;
+    const double2 m2 = m2_n;
+    prefetch_row(r + GPW);
+    const bool mine = r < r_hi && m2.x != 0.0;  // m2.x == 0 marks a long row (k_sweep_long / k_sweep_fix)
+    const uint32_t deg = e - b;                // 0 for long rows and rows past the range
+    // every edge below e_need must have landed
+    const uint32_t e_need = __reduce_max_sync(0xFFFFFFFFu, e);
+    const uint32_t w_need = (e_need + 31) >> 5;
+    while (pw < w_need) issue_window();  // cannot happen while the ring invariant holds; kept for safety
+    const uint32_t pending = pw - w_need;
+    if (pending == 0) cp_async_wait<0>();
+    else if (pending == 1) cp_async_wait<1>();
+    else if (pending == 2) cp_async_wait<2>();
+    else if (pending == 3) cp_async_wait<3>();
+    else if (pending <= 7) cp_async_wait<4>();
+    else if (pending <= 15) cp_async_wait<8>();
+    else cp_async_wait<16>();
+    __syncwarp();
+    Vec<VEC> a;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) a.v[c] = 0.0;
+    const uint32_t max_deg = __reduce_max_sync(0xFFFFFFFFu, deg);
+    for (uint32_t i = 0; i < max_deg; i += 4) {
+      double2 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] = make_double2(0.0, 0.0);
+        if (i + j < deg)
+          v[j] = *reinterpret_cast<const double2*>(ring + (size_t)((b + i + j) & (S - 1)) * ROWB + l8 * 16);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a.v[0] += v[j].x;
+        a.v[1] += v[j].y;
+      }
+    }
+    if (mine) epilogue2<LPR, VEC, FIRST, ALL>(p, r, l8, a, yl, m2, inv_tot, init, acc);
+    // refill: window w may be issued once every edge below (w + 1) * 32 - S has been consumed
+    __syncwarp();
+    const uint32_t consumed = min(__reduce_min_sync(0xFFFFFFFFu, b_n), e_hi);  // next block's first edge
+    while (pw < w_end && (pw + 1) * 32 <= consumed + S) issue_window();
+  }
+  cp_async_wait<0>();
+  if (p.n_peers) __threadfence_system();
+  block_reduce_nt<LPR, kAsyncThreads>(p, acc);
+}
+
 // Long-row tasks: one warp per task, 32 edges per step, group g takes edges
 // j*GPW+g; the GPW partial rows are combined with shuffles.  The next step's
 // indices are fetched before this step's rows.
@@ -592,7 +763,8 @@ template <int LPR, int VEC>
 __global__ void __launch_bounds__(kThreads) k_init(double* __restrict__ y, const uint32_t* __restrict__ outdeg,
                                                   uint64_t n_nodes, double damping, const double* __restrict__ init,
                                                   uint64_t row_lo, uint32_t rows_loc, double* __restrict__ mul_loc,
-                                                  double2* __restrict__ mul2_loc, double* __restrict__ red) {
+                                                  double2* __restrict__ mul2_loc,
+                                                  const uint64_t* __restrict__ in_ptr_loc, double* __restrict__ red) {
   constexpr int TP = LPR * VEC;
   __shared__ double sm[kThreads / 32][16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l8 = lane % LPR;
@@ -611,7 +783,9 @@ __global__ void __launch_bounds__(kThreads) k_init(double* __restrict__ y, const
       if (l8 == 0) {
         mul_loc[v - row_lo] = od ? m : 0.0;
         const bool has_out = od && m > 0.0;  // the sweeps' test (mul > 0)
-        mul2_loc[v - row_lo] = has_out ? make_double2(m, 1.0 / m) : make_double2(1.0, -1.0);
+        double2 rec = has_out ? make_double2(m, 1.0 / m) : make_double2(1.0, -1.0);
+        if (in_ptr_loc[v - row_lo + 1] - in_ptr_loc[v - row_lo] > kShortMax) rec.x = 0.0;  // long row marker
+        mul2_loc[v - row_lo] = rec;
       }
       if (od) {
 #pragma unroll
@@ -723,6 +897,49 @@ __global__ void k_local_ptr32(const uint64_t* __restrict__ in_ptr_loc, uint32_t 
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r < n_padded) out[r] = (uint32_t)in_ptr_loc[r <= rows_loc ? r : rows_loc];
 }
+// Short-row structures of the async kernel: sdeg[r] = in-degree if the row is short, else 0;
+// its exclusive scan is sptr; ssrc = the short rows' sources, compacted in row order.
+__global__ void k_short_deg(const uint64_t* __restrict__ in_ptr, uint32_t rows_loc, uint32_t* __restrict__ sdeg) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > rows_loc) return;
+  uint32_t d = 0;
+  if (r < rows_loc) {
+    const uint64_t deg = in_ptr[r + 1] - in_ptr[r];
+    d = deg <= kShortMax ? (uint32_t)deg : 0u;
+  }
+  sdeg[r] = d;
+}
+__global__ void k_short_compact(const uint64_t* __restrict__ in_ptr, const uint32_t* __restrict__ in_src,
+                                const uint32_t* __restrict__ sptr, uint32_t rows_loc, uint32_t pad,
+                                uint32_t* __restrict__ sptr_pad, uint32_t* __restrict__ ssrc) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows_loc) {
+    const uint32_t b = sptr[r], n = sptr[r + 1] - b;
+    const uint64_t from = in_ptr[r];
+    for (uint32_t i = 0; i < n; ++i) ssrc[b + i] = in_src[from + i];
+  } else if (r < (uint64_t)rows_loc + pad) {
+    sptr_pad[r + 1] = sptr[rows_loc];  // entries past rows_loc repeat the total
+  }
+}
+// Row range of every warp of the async kernel: cost(r) = sptr[r] + 3 r (edges + rows) is monotone;
+// boundary i = first r with cost(r) >= i * cost(R) / n_warps.
+__global__ void k_short_partition(const uint32_t* __restrict__ sptr, uint32_t rows_loc, uint32_t n_warps,
+                                  uint32_t* __restrict__ warp_rows) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n_warps) return;
+  if (i == n_warps) {
+    warp_rows[i] = rows_loc;
+    return;
+  }
+  const uint64_t total = (uint64_t)sptr[rows_loc] + 3ull * rows_loc;
+  const uint64_t want = total * i / n_warps;
+  uint32_t lo = 0, hi = rows_loc;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if ((uint64_t)sptr[mid] + 3ull * mid >= want) hi = mid; else lo = mid + 1;
+  }
+  warp_rows[i] = lo;
+}
 __global__ void k_count_tasks(const uint64_t* __restrict__ in_ptr, uint32_t rows_loc, uint32_t* __restrict__ nt,
                               uint32_t* __restrict__ nf) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -781,7 +998,10 @@ struct PagerankState {
   ss::DevBuf<uint64_t> in_ptr;   // [rows_loc + 1]
   ss::DevBuf<uint32_t> in_ptr32; // [rows_loc + 1 + ptr32_pad], only when E_loc < 2^32
   uint64_t ptr32_pad = 0;        // 0: no 32-bit copy
-  ss::DevBuf<double2> mul2;      // [rows_loc] {m, 1/m} or {1, -1}
+  ss::DevBuf<double2> mul2;      // [rows_loc] {m, 1/m} or {1, -1}; m = 0 marks a long row
+  ss::DevBuf<uint32_t> sptr, ssrc, warp_rows;  // async short-row kernel: short-only CSR and warp row ranges
+  bool have_short = false;
+  uint32_t E_short = 0;
   ss::DevBuf<uint32_t> in_src;   // [E_loc]
   ss::DevBuf<LongTask> tasks;
   ss::DevBuf<FixRow> fix;
@@ -804,7 +1024,7 @@ struct PagerankState {
   // load-time scratch, kept between loads (grow-only)
   struct Scratch {
     ss::DevBuf<uint64_t> row_ptr;
-    ss::DevBuf<uint32_t> col, src, col_sorted, src_sorted, nt, nf, toff, foff, keys, keys_out, order, order_out;
+    ss::DevBuf<uint32_t> col, src, col_sorted, src_sorted, nt, nf, toff, foff, keys, keys_out, order, order_out, sdeg;
     ss::DevBuf<unsigned long long> in_ptr_full, bounds;
     ss::DevBuf<int> bad;
     ss::DevBuf<char> tmp;
@@ -1022,6 +1242,31 @@ SS_API int ss_graph_load_csr(ss_engine* e, uint64_t n_nodes, uint64_t n_edges, c
     s->ptr32_pad = pad;
   }
 
+  // short-only CSR of the cp.async ring kernel: measured equal to the lean register kernel at
+  // configs[1] (1.39 vs 1.38 ms: both sit at the chip's random 128-byte row rate), so it is opt-in
+  // and its structures are only built on request
+  s->have_short = false;
+  const char* short_env = getenv("SS_PR_SHORT");
+  if (short_env && !strcmp(short_env, "async") && s->E_loc < 0xFFFFFFFFull && s->rows_loc) {
+    const uint32_t R = s->rows_loc, pad = 64;
+    SS_TRY(sc.sdeg.reserve((size_t)R + 1));
+    SS_TRY(s->sptr.reserve((size_t)R + 2 + pad));
+    k_short_deg<<<ss::div_up((uint64_t)R + 1, 256), 256, 0, st>>>(s->in_ptr.p, R, sc.sdeg.p);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, sc.sdeg.p, s->sptr.p, (int)(R + 1), st);
+    SS_TRY(sc.tmp.reserve(tmp_bytes));
+    tmp_bytes = sc.tmp.n;
+    SS_CUDA(cub::DeviceScan::ExclusiveSum(sc.tmp.p, tmp_bytes, sc.sdeg.p, s->sptr.p, (int)(R + 1), st));
+    uint32_t e_short = 0;
+    SS_CUDA(cudaMemcpyAsync(&e_short, s->sptr.p + R, 4, cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaStreamSynchronize(st));
+    s->E_short = e_short;
+    SS_TRY(s->ssrc.reserve((size_t)e_short + 64));
+    k_short_compact<<<ss::div_up((uint64_t)R + pad, 256), 256, 0, st>>>(s->in_ptr.p, s->in_src.p, s->sptr.p, R, pad,
+                                                                       s->sptr.p, s->ssrc.p);
+    s->have_short = true;
+  }
+
   // long-row tasks and fix rows
   s->n_tasks = s->n_fix = 0;
   if (s->rows_loc) {
@@ -1129,8 +1374,33 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
     if (need > s->ptr32_pad) lean = false;
   }
   if (lean) occ_short = occ_short32;
-  const uint32_t grid_short =
+  // async gather ring (SS_PR_SHORT=async at load and run time): needs the short-only CSR and a
+  // 16-byte-per-lane shape
+  const bool want_async = short_env && !strcmp(short_env, "async");
+  const bool use_async = want_async && s->have_short && shape.vec == 2 && R > 0;
+  const size_t async_smem = (size_t)(kAsyncThreads / 32) * kRingBytes;
+  uint32_t grid_short =
       std::max(1u, std::min<uint32_t>(n_row_blocks, (uint32_t)(e->sm_count * std::max(1, occ_short))));
+  if (use_async) {
+    int occ_async = 1;
+    dispatch_shape(shape, [&](auto lpr, auto) {
+      constexpr int L = decltype(lpr)::value;
+      auto set = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)async_smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_async, kern, kAsyncThreads, async_smem);
+      };
+      set(k_sweep_short_async<L, true, true>);
+      set(k_sweep_short_async<L, true, false>);
+      set(k_sweep_short_async<L, false, true>);
+      set(k_sweep_short_async<L, false, false>);
+      return SS_OK;
+    });
+    SS_CUDA(cudaGetLastError());
+    grid_short = std::max(1u, std::min<uint32_t>(ss::div_up(R, 64), (uint32_t)(e->sm_count * std::max(1, occ_async))));
+    const uint32_t n_warps = grid_short * (kAsyncThreads / 32);
+    SS_TRY(s->warp_rows.reserve((size_t)n_warps + 1));
+    k_short_partition<<<ss::div_up((uint64_t)n_warps + 1, 256), 256, 0, st>>>(s->sptr.p, R, n_warps, s->warp_rows.p);
+  }
   const uint32_t grid_long = std::max(
       1u, std::min<uint32_t>(ss::div_up(s->n_tasks, kThreads / 32), (uint32_t)(e->sm_count * std::max(1, occ_long))));
   const uint32_t grid_fix = std::max(1u, std::min<uint32_t>(s->n_fix, (uint32_t)e->sm_count * 8));
@@ -1171,7 +1441,7 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
   int rc = dispatch_shape(shape, [&](auto lpr, auto vec) {
     constexpr int L = decltype(lpr)::value, V = decltype(vec)::value;
     k_init<L, V><<<grid_init, kThreads, 0, st>>>(s->y[0].p, s->outdeg.p, N, damping, s->init.p, s->row_lo, R, s->mul.p,
-                                             s->mul2.p, s->red.p);
+                                             s->mul2.p, s->in_ptr.p, s->red.p);
     return SS_OK;
   });
   SS_TRY(rc);
@@ -1196,6 +1466,9 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
     p.mul = s->mul.p;
     p.in_ptr32 = s->in_ptr32.p;
     p.mul2 = s->mul2.p;
+    p.sptr = s->sptr.p;
+    p.ssrc = s->ssrc.p;
+    p.warp_rows = s->warp_rows.p;
     p.inv_tot = s->tot.p;
     p.init = s->init.p;
     p.row_lo = s->row_lo;
@@ -1210,8 +1483,16 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
       constexpr int L = decltype(lpr)::value, V = decltype(vec)::value;
       SweepParams q = p;
       q.red = s->red.p;
-      if (lean) {
-        const bool all = active == all_topics && T == TP;  // padded columns stay frozen through the mask
+      const bool all = active == all_topics && T == TP;  // padded columns stay frozen through the mask
+      if (use_async) {
+        if (p.first) {
+          if (all) k_sweep_short_async<L, true, true><<<grid_short, kAsyncThreads, async_smem, st>>>(q);
+          else k_sweep_short_async<L, true, false><<<grid_short, kAsyncThreads, async_smem, st>>>(q);
+        } else {
+          if (all) k_sweep_short_async<L, false, true><<<grid_short, kAsyncThreads, async_smem, st>>>(q);
+          else k_sweep_short_async<L, false, false><<<grid_short, kAsyncThreads, async_smem, st>>>(q);
+        }
+      } else if (lean) {
         if (p.first) {
           if (all) k_sweep_short32<L, V, true, true><<<grid_short, kThreads, 0, st>>>(q, n_row_blocks);
           else k_sweep_short32<L, V, true, false><<<grid_short, kThreads, 0, st>>>(q, n_row_blocks);

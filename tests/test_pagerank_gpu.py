@@ -53,19 +53,26 @@ def test_random_graphs(engine, n, e, seed):
     assert np.isfinite(got).all() and (got > 0).all()
 
 
-def test_lean_short_row_kernel_matches_legacy_bitwise(engine, monkeypatch):
-    # k_sweep_short32 (32-bit padded row pointers, packed scale record) must reproduce the first
-    # short-row kernel bit for bit: same gather order, same epilogue expressions.  Frozen topics
-    # (different num_pages -> different sweep counts) exercise the masked instantiations.
+def test_short_row_kernels_agree_bitwise(engine, monkeypatch):
+    # The three short-row kernels -- first version (legacy), lean registers (k_sweep_short32, the
+    # default) and the opt-in cp.async gather ring (k_sweep_short_async) -- use the same gather order and the same
+    # epilogue expressions, so their results must be identical bit for bit.  Frozen topics (different
+    # num_pages -> different sweep counts) exercise the masked instantiations; the topic counts cover
+    # every lane shape.
     g = synth.graph(60000, 900000, seed=13)
+    monkeypatch.setenv("SS_PR_SHORT", "async")  # the ring kernel's short-only CSR is built at load on request
     engine.graph_load_csr(g.row_ptr, g.col_idx)
-    for npg, eps in ((synth.topics(16), 1e-9), ([3, 50000, 7, 1000000, 11], 1e-13)):
-        monkeypatch.setenv("SS_PR_SHORT", "legacy")
-        a, ia, _ = engine.pagerank(0.75, eps, npg)
+    cases = [(synth.topics(16), 1e-9), ([3, 50000, 7, 1000000, 11], 1e-13), (synth.topics(8), 1e-9),
+             (synth.topics(3), 1e-9), ([50000, 9], 1e-11), ([12345], 1e-9)]
+    for npg, eps in cases:
+        out = {}
+        for mode in ("legacy", "lean", "async"):
+            monkeypatch.setenv("SS_PR_SHORT", mode)
+            out[mode] = engine.pagerank(0.75, eps, npg)
         monkeypatch.delenv("SS_PR_SHORT")
-        b, ib, _ = engine.pagerank(0.75, eps, npg)
-        assert ia.tolist() == ib.tolist()
-        assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+        for mode in ("lean", "async"):
+            assert out[mode][1].tolist() == out["legacy"][1].tolist(), mode
+            assert np.array_equal(out[mode][0].view(np.uint64), out["legacy"][0].view(np.uint64)), mode
 
 
 def test_damping_085_and_tight_eps(engine):
