@@ -910,8 +910,8 @@ __global__ void k_short_deg(const uint64_t* __restrict__ in_ptr, uint32_t rows_l
   sdeg[r] = d;
 }
 __global__ void k_short_compact(const uint64_t* __restrict__ in_ptr, const uint32_t* __restrict__ in_src,
-                                const uint32_t* __restrict__ sptr, uint32_t rows_loc, uint32_t pad,
-                                uint32_t* __restrict__ sptr_pad, uint32_t* __restrict__ ssrc) {
+                                const uint32_t* sptr, uint32_t rows_loc, uint32_t pad, uint32_t* sptr_pad,
+                                uint32_t* __restrict__ ssrc) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r < rows_loc) {
     const uint32_t b = sptr[r], n = sptr[r + 1] - b;

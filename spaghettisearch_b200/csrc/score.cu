@@ -33,7 +33,6 @@ namespace {
 constexpr int kT = 256;        // threads per CTA
 constexpr int kRange = 2048;   // docs per sub-range
 constexpr int kCand = 1024;    // candidate buffer = doc slots finished per round
-constexpr int kBatch = kCand;  // doc slots fetched together in the finalize step
 constexpr int kMaxK = 128;
 constexpr int kMaxKw = 64;     // keyword tokens per query handled in-kernel
 constexpr int kMaxPh = 32;     // phrase tokens per query handled in-kernel
@@ -57,7 +56,7 @@ struct ScoreParams {
   int prefetch_meta;       // issue L1 prefetches of the screening records per sub-range
   const uint32_t* narrow;  // [list][n_slabs+1] posting offset (from the term's row start) of every slab boundary
   uint32_t sort_max;     // slabs with at most this many postings take the sort path (<= kSortMax)
-  int screen_ok;         // every weight is finite and >= 0: fp32 sums bound the exact ones (no cancellation)
+  int owner_path;        // phrase-free sparse slabs: lookups in the sorted lists instead of a sort
   const double* sqd;     // [D] blend term for a shared topic vector, or NULL
   const double* pr;      // [D][T] for per-query topic vectors
   const double* probs;   // [n_q][T] when per-query
@@ -74,6 +73,8 @@ struct ScoreParams {
   double* part_pr;
   uint32_t* part_count;  // [n_q][n_slabs]
   unsigned long long* stats;  // [0] postings scanned, [1] docs matched
+  unsigned long long* qthr;   // [n_q] running per-query bound (score key), zeroed per batch
+  int use_qthr;
 };
 
 // Total order of results: FinalRank descending, ties by ascending doc id, NaN
@@ -115,11 +116,13 @@ struct Smem {
   uint32_t cand_doc[kCand];
   uint32_t top_doc[2][kMaxK];
   uint32_t bits[kRange / 32];
-  uint16_t surv[kRange];  // slots of the docs that survived the fp32 screening of a sub-range
-  uint32_t n_cand, n_ent, n_surv, top_n, top_buf;
+  uint16_t mlist[kRange];  // slots of the sub-range's matched docs, in first-touch order
+  uint32_t n_cand, n_ent, n_list, top_n, top_buf;
   unsigned long long thr_key, piv_key;
   uint32_t thr_doc, piv_doc;
-  float thr_f;  // fp32 lower bound of the k-th best score (-inf until k results exist)
+  float thr_f;  // fp32 lower bound of the score a doc needs: max(local k-th best, the query's running bound)
+  unsigned long long gkey;  // the query's running bound (score key of some slab's k-th best), 0 = none
+  float gthr_f;             // its score rounded down to fp32 (-inf when none)
 };
 
 // Union of the running top-k and the candidate buffer -> new running top-k by
@@ -189,7 +192,7 @@ __device__ void merge_candidates(Smem& s, uint32_t k) {
       s.thr_doc = s.top_doc[nb][k - 1];
       const double thr = key_score(s.thr_key);
       // NaN as k-th best (only NaN scores so far) must not filter anything
-      s.thr_f = isnan(thr) ? -__int_as_float(0x7f800000) : __double2float_rd(thr);
+      s.thr_f = isnan(thr) ? s.gthr_f : fmaxf(s.gthr_f, __double2float_rd(thr));
     }
   }
   __syncthreads();
@@ -200,6 +203,16 @@ __device__ void merge_candidates(Smem& s, uint32_t k) {
 constexpr uint32_t kSortMax = 2 * kRange;  // entries; the buffer aliases the two accumulator arrays
 __device__ __forceinline__ unsigned long long make_entry(uint32_t off, uint32_t seq, float w) {
   return ((unsigned long long)off << 40) | ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(w);
+}
+
+// First posting to touch a doc slot of the sub-range appends it to the matched list, so that the
+// finalize step costs what the matches cost (the first version walked the whole bitmap: ~760
+// warp instructions per warp and sub-range whatever the density, the dominant cost for all but
+// the densest lists).
+__device__ __forceinline__ void mark_matched(Smem& s, uint32_t slot) {
+  const uint32_t bit = 1u << (slot & 31);
+  const uint32_t old = atomicOr(&s.bits[slot >> 5], bit);
+  if (!(old & bit)) s.mlist[atomicAdd(&s.n_list, 1u) & (kRange - 1)] = (uint16_t)slot;
 }
 
 // phrase.go:53-109 for one table over the lists' current ranges [cur, hi).  Lists
@@ -268,7 +281,7 @@ __device__ void apply_phrase(const ScoreParams& p, Smem& s, int tb, uint32_t l0,
       ent[atomicAdd(&s.n_ent, 1u)] = make_entry(slot, seq, sum);
     } else {
       s.acc[tb][slot] = __dadd_rn(s.acc[tb][slot], (double)sum);
-      atomicOr(&s.bits[slot >> 5], 1u << (slot & 31));
+      mark_matched(s, slot);
     }
   }
 }
@@ -327,6 +340,7 @@ __device__ __forceinline__ void finish_exact(const ScoreParams& p, Smem& s, uint
   const double fin =
       __dmul_rn(__dadd_rn(__dadd_rn(__dmul_rn(0.33, m.sqd), __dmul_rn(0.38, title)), __dmul_rn(0.29, body)), 100.0);
   const unsigned long long key = score_key(fin);
+  if (key < s.gkey) return;  // below another slab's k-th best: cannot be in the query's top k
   if (s.top_n < k || beats(key, (uint32_t)doc, s.thr_key, s.thr_doc)) {
     const uint32_t j = atomicAdd(&s.n_cand, 1u);
     s.cand_key[j] = key;
@@ -336,32 +350,8 @@ __device__ __forceinline__ void finish_exact(const ScoreParams& p, Smem& s, uint
 __device__ __forceinline__ void finish_doc(const ScoreParams& p, Smem& s, uint32_t q, uint64_t doc, double tr,
                                            double br, const float4& m32, float qf_inv, float blend_scale,
                                            double qm, uint32_t k) {
-  if (s.top_n >= k && screened_out(s, (float)tr, (float)br, m32, qf_inv, blend_scale)) return;
+  if (screened_out(s, (float)tr, (float)br, m32, qf_inv, blend_scale)) return;
   finish_exact(p, s, q, doc, tr, br, qm, k);
-}
-
-// fp32 variant for the screened path: lists may be applied concurrently (shared-memory float atomics)
-__device__ __forceinline__ void accumulate_list_f32(const TableView& tv, Smem& s, float* af, unsigned long long x0,
-                                                    unsigned long long x1, uint64_t d0) {
-  constexpr int U = 4;
-  for (unsigned long long x = x0 + threadIdx.x; x < x1; x += (unsigned long long)U * kT) {
-    uint32_t d[U];
-    float w[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const unsigned long long xx = x + (unsigned long long)u * kT;
-      const bool ok = xx < x1;
-      d[u] = ok ? tv.doc_ids[xx] : 0xFFFFFFFFu;
-      w[u] = ok ? tv.w[xx] : 0.0f;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (d[u] == 0xFFFFFFFFu) continue;
-      const uint32_t slot = (uint32_t)(d[u] - d0);
-      atomicAdd(&af[slot], w[u]);
-      atomicOr(&s.bits[slot >> 5], 1u << (slot & 31));
-    }
-  }
 }
 
 // One list's postings of the sub-range into the accumulators; a list holds a doc at
@@ -385,7 +375,7 @@ __device__ __forceinline__ void accumulate_list(const TableView& tv, Smem& s, in
       if (d[u] == 0xFFFFFFFFu) continue;
       const uint32_t slot = (uint32_t)(d[u] - d0);
       s.acc[tb][slot] = __dadd_rn(s.acc[tb][slot], (double)w[u]);
-      atomicOr(&s.bits[slot >> 5], 1u << (slot & 31));
+      mark_matched(s, slot);
     }
   }
 }
@@ -470,6 +460,84 @@ __device__ void sort_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
   }
 }
 
+// Sparse (query, slab) pairs without a phrase: the keyword lists are staged in shared memory as
+// they are -- every list is already sorted by doc -- and each posting looks its doc up in the
+// other lists by binary search.  The posting of the FIRST list that holds the doc owns it: it
+// folds the doc's weights in list (= query-token) order, which is the order of the reference's
+// sums, and finishes the doc.  No sort, no barriers inside the loop: the bitonic sort this
+// replaces cost ~100 ps per posting against ~10 ps in the dense path (78 block barriers per
+// 4096 entries), and 44 % of the benchmark's query tokens take this path.
+__device__ void owner_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t slab_lo, uint32_t n_kw, double qm,
+                           float qf_inv, float blend_scale, uint32_t k, unsigned long long& n_postings,
+                           unsigned long long& n_matched) {
+  uint32_t* soff = reinterpret_cast<uint32_t*>(&s.acc[0][0]);  // [kSortMax] doc offset in the slab
+  float* sw = reinterpret_cast<float*>(&s.acc[1][0]);          // [kSortMax] weight
+  const uint32_t tid = threadIdx.x, n_lists = 2 * n_kw;
+  if (tid == 0) {
+    uint32_t run = 0;
+    for (uint32_t l = 0; l < n_lists; ++l) {
+      s.bounds[l] = run;
+      run += s.len[l];
+    }
+    s.bounds[n_lists] = run;
+  }
+  __syncthreads();
+  const uint32_t total = s.bounds[n_lists];
+  // stage: list by list, coalesced
+  for (uint32_t l = 0; l < n_lists; ++l) {
+    const uint32_t len = s.len[l];
+    if (!len) continue;
+    const TableView& tv = p.tab[l & 1];
+    const unsigned long long at = s.base[l];
+    const uint32_t o = s.bounds[l];
+    for (uint32_t i = tid; i < len; i += kT) {
+      soff[o + i] = (uint32_t)(tv.doc_ids[at + i] - slab_lo);
+      sw[o + i] = tv.w[at + i];
+    }
+  }
+  if (tid == 0) n_postings += total;
+  __syncthreads();
+  // position of doc offset `off` in list j, or kNoDoc
+  auto find = [&](uint32_t j, uint32_t off) -> uint32_t {
+    uint32_t lo = s.bounds[j], hi = s.bounds[j + 1];
+    const uint32_t end = hi;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (soff[mid] < off) lo = mid + 1; else hi = mid;
+    }
+    return (lo < end && soff[lo] == off) ? lo : kNoDoc;
+  };
+  for (uint32_t r0 = 0; r0 < total; r0 += kCand) {
+    const uint32_t r1 = min(total, r0 + kCand);
+    for (uint32_t idx = r0 + tid; idx < r1; idx += kT) {
+      uint32_t lo = 0, hi = n_lists;  // last l with bounds[l] <= idx
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s.bounds[mid] <= idx) lo = mid; else hi = mid;
+      }
+      const uint32_t l = lo, off = soff[idx];
+      bool owner = true;
+      for (uint32_t j = 0; j < l && owner; ++j) owner = find(j, off) == kNoDoc;
+      if (!owner) continue;
+      double tr = 0.0, br = 0.0;
+      {
+        const double w = (double)sw[idx];
+        if (l & 1u) br = w; else tr = w;
+      }
+      for (uint32_t j = l + 1; j < n_lists; ++j) {
+        const uint32_t at = find(j, off);
+        if (at == kNoDoc) continue;
+        const double w = (double)sw[at];
+        if (j & 1u) br = __dadd_rn(br, w); else tr = __dadd_rn(tr, w);
+      }
+      ++n_matched;
+      finish_doc(p, s, q, slab_lo + off, tr, br, p.meta32[slab_lo + off], qf_inv, blend_scale, qm, k);
+    }
+    __syncthreads();
+    if (s.n_cand) merge_candidates(s, k);
+  }
+}
+
 __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
@@ -489,12 +557,21 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
   if (tid == 0) {
     s.n_cand = 0;
     s.n_ent = 0;
-    s.n_surv = 0;
+    s.n_list = 0;
     s.top_n = 0;
     s.top_buf = 0;
     s.thr_key = 0;
     s.thr_doc = kNoDoc;
-    s.thr_f = -__int_as_float(0x7f800000);
+    // Running bound of the query: CTAs are launched slab-major, so by the time slab j of a query
+    // starts, earlier slabs have usually published their k-th best score.  A doc scoring strictly
+    // below ANY slab's k-th best cannot be among the query's k best, so it is dropped here exactly
+    // as the per-slab threshold drops it; ties are kept (the doc id decides them in k_merge).  The
+    // result does not depend on which bound a CTA happens to see.
+    const unsigned long long g = p.use_qthr ? *reinterpret_cast<volatile unsigned long long*>(p.qthr + q) : 0ull;
+    const double gs = key_score(g);
+    s.gkey = g;
+    s.gthr_f = (g == 0ull || isnan(gs)) ? -__int_as_float(0x7f800000) : __double2float_rd(gs);
+    s.thr_f = s.gthr_f;
   }
   // narrow every list to the slab
   for (uint32_t l = tid; l < n_lists; l += kT) {
@@ -533,6 +610,8 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
 
   if (work == 0) {
     // nothing of this query lives in this slab
+  } else if (work <= p.sort_max && n_ph == 0 && p.owner_path) {
+    owner_path(p, s, q, slab_lo, n_kw, qm, qf_inv, blend_scale, k, n_postings, n_matched);
   } else if (work <= p.sort_max && p.slab_docs <= (1ull << 24)) {
     sort_path(p, s, q, slab_lo, n_kw, n_ph, qm, qf_inv, blend_scale, k, n_postings, n_matched);
   } else {
@@ -541,6 +620,7 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
     s.acc[1][i] = 0.0;
   }
   for (uint32_t i = tid; i < kRange / 32; i += kT) s.bits[i] = 0;
+  uint32_t list_done = 0;  // n_list at the end of the previous sub-range (uniform)
   // Sub-range boundaries of every list are found up front, all threads searching
   // in parallel (one dependent-load chain per CTA pass instead of one per sub-range).
   const uint32_t n_sub = (uint32_t)((slab_hi - slab_lo + kRange - 1) / kRange);
@@ -560,79 +640,6 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
     // list l covers postings [base + bounds[l][sj], base + bounds[l][sj+1]) in this sub-range
     auto lo_of = [&](uint32_t l) { return s.base[l] + s.bounds[l * (nb + 1) + sj]; };
     auto hi_of = [&](uint32_t l) { return s.base[l] + s.bounds[l * (nb + 1) + sj + 1]; };
-
-    // Screened path (keyword-only queries once k exact results exist): all lists are applied
-    // concurrently into fp32 accumulators -- no per-token barriers -- and only the docs whose fp32
-    // bound reaches the running k-th best are re-evaluated exactly: one warp per survivor looks
-    // the doc up in every list (lane = list) and folds the weights in fp64 in token order, so the
-    // exact sums are the ones of the token-ordered path.
-    if (p.screen_ok && n_ph == 0 && s.top_n >= k) {
-      float* af = reinterpret_cast<float*>(&s.acc[0][0]);  // [2][kRange] fp32 view of the zeroed accumulators
-      const uint32_t lane = tid & 31, warp = tid >> 5;
-      unsigned long long cnt = 0;
-      for (uint32_t l = 0; l < 2 * n_kw; ++l) {
-        const unsigned long long x0 = lo_of(l), x1 = hi_of(l);
-        if (x1 == x0) continue;
-        cnt += x1 - x0;
-        accumulate_list_f32(p.tab[l & 1], s, af + (l & 1) * kRange, x0, x1, d0);
-      }
-      if (cnt == 0) continue;  // uniform
-      if (tid == 0) n_postings += cnt;
-      __syncthreads();
-      constexpr int kWordsPerWarpS = kRange / 32 / (kT / 32);
-#pragma unroll 2
-      for (int r = 0; r < kWordsPerWarpS; ++r) {
-        const uint32_t wi = warp + r * (kT / 32);
-        const uint32_t word = s.bits[wi];
-        if (!word) continue;  // warp uniform
-        __syncwarp();
-        if (lane == 0) s.bits[wi] = 0;
-        if (!((word >> lane) & 1u)) continue;
-        const uint32_t slot = wi * 32 + lane;
-        const float4 m32 = p.meta32[d0 + slot];
-        const float tr = af[slot], br = af[kRange + slot];
-        af[slot] = 0.0f;
-        af[kRange + slot] = 0.0f;
-        ++n_matched;
-        if (!screened_out(s, tr, br, m32, qf_inv, blend_scale)) s.surv[atomicAdd(&s.n_surv, 1u)] = (uint16_t)slot;
-      }
-      __syncthreads();
-      const uint32_t ns = s.n_surv;
-      for (uint32_t i = warp; i < ns; i += kT / 32) {
-        const uint32_t doc = (uint32_t)(d0 + s.surv[i]);
-        double tr = 0.0, br = 0.0;
-        for (uint32_t l0 = 0; l0 < 2 * n_kw; l0 += 32) {
-          const uint32_t l = l0 + lane;
-          float wv = 0.0f;
-          bool found = false;
-          if (l < 2 * n_kw) {
-            const TableView& tv = p.tab[l & 1];
-            unsigned long long a = lo_of(l), b = hi_of(l);
-            const unsigned long long hi_l = b;
-            while (a < b) {
-              const unsigned long long mid = (a + b) >> 1;
-              if (tv.doc_ids[mid] < doc) a = mid + 1; else b = mid;
-            }
-            if (a < hi_l && tv.doc_ids[a] == doc) {
-              found = true;
-              wv = tv.w[a];
-            }
-          }
-          const unsigned fm = __ballot_sync(0xFFFFFFFFu, found);
-          const uint32_t nl = min(32u, 2 * n_kw - l0);
-          for (uint32_t j = 0; j < nl; ++j) {
-            if (!((fm >> j) & 1u)) continue;
-            const double wj = (double)__shfl_sync(0xFFFFFFFFu, wv, j);
-            if ((l0 + j) & 1u) br = __dadd_rn(br, wj); else tr = __dadd_rn(tr, wj);
-          }
-        }
-        if (lane == 0) finish_exact(p, s, q, doc, tr, br, qm, k);
-      }
-      __syncthreads();
-      if (tid == 0) s.n_surv = 0;
-      if (s.n_cand) merge_candidates(s, k);
-      continue;
-    }
 
     // the screening records of this sub-range (kRange x 16 B, one 128-byte line per thread) are
     // requested now so that they arrive in L1 while the postings are being applied
@@ -671,62 +678,50 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
     if (!any) continue;  // uniform
     __syncthreads();
 
-    // finish the matched docs, word by word of the bitmap (work follows the matches);
-    // a lane's docs of one batch are fetched together before any of them is scored
-    const uint32_t lane = tid & 31, warp = tid >> 5;
-    constexpr int kWordsPerWarp = kBatch / 32 / (kT / 32);
-    for (uint32_t w0 = 0; w0 < kRange / 32; w0 += kBatch / 32) {
-      bool has[kWordsPerWarp];
-      uint32_t slot[kWordsPerWarp];
-      float4 meta[kWordsPerWarp];
-      double tr[kWordsPerWarp], br[kWordsPerWarp];
-      uint32_t any_word = 0;
+    // finish the matched docs from the first-touch list, kCand (the candidate buffer's capacity)
+    // per round; a thread's docs of a round are fetched together before any of them is scored.
+    // n_list only grows (ring index), so nothing but the bitmap needs a reset.
+    const uint32_t list_end = s.n_list;
+    if (tid == 0) n_matched += list_end - list_done;
+    if (tid < kRange / 32) s.bits[tid] = 0;  // not read again before the barrier below
+    const float4* meta_base = p.meta32 + d0;
+    constexpr int kPer = kCand / kT;
+    for (uint32_t r0 = list_done; r0 != list_end; r0 += min((uint32_t)kCand, list_end - r0)) {
+      bool has[kPer];
+      uint32_t slot[kPer];
+      float4 meta[kPer];
+      double tr[kPer], br[kPer];
 #pragma unroll
-      for (int r = 0; r < kWordsPerWarp; ++r) {
-        const uint32_t wi = w0 + warp + r * (kT / 32);
-        const uint32_t word = s.bits[wi];
-        any_word |= word;
-        has[r] = (word >> lane) & 1u;
-        slot[r] = wi * 32 + lane;
+      for (int c = 0; c < kPer; ++c) {
+        const uint32_t i = tid + c * kT;
+        has[c] = i < list_end - r0;
+        slot[c] = has[c] ? s.mlist[(r0 + i) & (kRange - 1)] : 0u;
       }
-      if (any_word) {  // warp uniform: something matched in this warp's words
-        const float4* meta_base = p.meta32 + d0;
 #pragma unroll
-        for (int r = 0; r < kWordsPerWarp; ++r) {
-          meta[r] = meta_base[has[r] ? slot[r] : 0u];
-          tr[r] = s.acc[0][slot[r]];
-          br[r] = s.acc[1][slot[r]];
-        }
-        // the running k-th best only changes in merge_candidates, i.e. between batches
-        const float thr_f = s.top_n >= k ? s.thr_f : -__int_as_float(0x7f800000);
-        __syncwarp();
+      for (int c = 0; c < kPer; ++c) {
+        if (!has[c]) continue;
+        meta[c] = meta_base[slot[c]];
+        tr[c] = s.acc[0][slot[c]];
+        br[c] = s.acc[1][slot[c]];
+      }
+      // the running k-th best only changes in merge_candidates, i.e. between rounds
+      const float thr_f = s.thr_f;
 #pragma unroll
-        for (int r = 0; r < kWordsPerWarp; ++r) {
-          const uint32_t wi = w0 + warp + r * (kT / 32);
-          if (lane == 0) {
-            n_matched += __popc(s.bits[wi]);
-            s.bits[wi] = 0;
-          }
-          if (!has[r]) continue;
-          s.acc[0][slot[r]] = 0.0;
-          s.acc[1][slot[r]] = 0.0;
-          // screening (see finish_doc): sc_a/sc_t/sc_b fold the blend weights, 1/|q| and the x100
-          const float a = sc_a * meta[r].z;
-          const float b = tr[r] != 0.0 ? sc_t * ((float)tr[r] * meta[r].x) : 0.0f;
-          const float c = br[r] != 0.0 ? sc_b * ((float)br[r] * meta[r].y) : 0.0f;
-          if ((a + b + c) + (fabsf(a) + fabsf(b) + fabsf(c)) * 1e-4f + 1e-30f < thr_f) continue;
-          finish_exact(p, s, q, d0 + slot[r], tr[r], br[r], qm, k);
-        }
+      for (int c = 0; c < kPer; ++c) {
+        if (!has[c]) continue;
+        s.acc[0][slot[c]] = 0.0;
+        s.acc[1][slot[c]] = 0.0;
+        // screening (see finish_doc): sc_a/sc_t/sc_b fold the blend weights, 1/|q| and the x100
+        const float a = sc_a * meta[c].z;
+        const float b = tr[c] != 0.0 ? sc_t * ((float)tr[c] * meta[c].x) : 0.0f;
+        const float cc = br[c] != 0.0 ? sc_b * ((float)br[c] * meta[c].y) : 0.0f;
+        if ((a + b + cc) + (fabsf(a) + fabsf(b) + fabsf(cc)) * 1e-4f + 1e-30f < thr_f) continue;
+        finish_exact(p, s, q, d0 + slot[c], tr[c], br[c], qm, k);
       }
-      if (kBatch < kRange) {  // the candidate buffer holds one batch: merge between batches
-        __syncthreads();
-        if (s.n_cand) merge_candidates(s, k);
-      }
-    }
-    if (kBatch >= kRange) {
-      __syncthreads();  // accumulators and bitmap are clean again; candidates are complete
+      __syncthreads();  // accumulators of this round are clean, candidates are complete
       if (s.n_cand) merge_candidates(s, k);
     }
+    list_done = list_end;
   }
   }
   }
@@ -755,7 +750,10 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
       p.part_pr[base + j] = 0.0;
     }
   }
-  if (tid == 0) p.part_count[(size_t)q * p.n_slabs + slab] = tn;
+  if (tid == 0) {
+    p.part_count[(size_t)q * p.n_slabs + slab] = tn;
+    if (p.use_qthr && tn == k && s.top_key[tb][k - 1] > s.gkey) atomicMax(p.qthr + q, s.top_key[tb][k - 1]);
+  }
   // stats: warp-reduce then one atomic per warp
   for (int o = 16; o; o >>= 1) {
     n_postings += __shfl_xor_sync(0xFFFFFFFFu, n_postings, o);
@@ -875,12 +873,6 @@ __global__ void k_meta32(const double* __restrict__ mag_t, const double* __restr
   out[d] = m;
 }
 
-// screen_ok: every weight finite and >= 0 (then fp32 partial sums cannot cancel)
-__global__ void k_weights_ok(const float* __restrict__ w, uint64_t P, int* __restrict__ bad) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < P && !(w[i] >= 0.0f && w[i] < 3.0e38f)) *bad = 1;
-}
-
 TableView view_of(const TableState& tb) {
   TableView v{};
   if (!tb.loaded) return v;
@@ -972,6 +964,7 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   SS_TRY(ws_reserve(ws.out_pr, n_q * k));
   SS_TRY(ws_reserve(ws.out_count, n_q));
   SS_TRY(ws_reserve(ws.stats, 2));
+  SS_TRY(ws_reserve(ws.qthr, n_q));
   const uint64_t n_narrow = 2 * (n_kw + n_ph) * (n_slabs + 1);
   SS_TRY(ws_reserve(ws.narrow, n_narrow));
   // a table that was never loaded behaves as an empty one with zero norms
@@ -1004,6 +997,7 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
     if (n_ph) SS_CUDA(cudaMemcpyAsync(ws.ph.p, ph_terms, n_ph * 4, cudaMemcpyHostToDevice, st));
   }
   SS_CUDA(cudaMemsetAsync(ws.stats.p, 0, 16, st));
+  SS_CUDA(cudaMemsetAsync(ws.qthr.p, 0, n_q * 8, st));
   // blend term: one pass over forw[3] for a shared topic vector, cached across batches
   const double* sqd_ptr = nullptr;
   if (shared_blend) {
@@ -1034,27 +1028,10 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
     }
   }
 
-  if (!ix->wcheck_valid) {
-    ss::DevBuf<int> d_bad;
-    SS_TRY(d_bad.alloc(1));
-    SS_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
-    for (int tb = 0; tb < 2; ++tb)
-      if (ix->tab[tb].loaded && ix->tab[tb].P)
-        k_weights_ok<<<ss::div_up(ix->tab[tb].P, 256), 256, 0, st>>>(ix->tab[tb].w.p, ix->tab[tb].P, d_bad.p);
-    int bad = 0;
-    SS_CUDA(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    SS_CUDA(cudaStreamSynchronize(st));
-    ix->weights_nonneg = !bad;
-    ix->wcheck_valid = true;
-    launches += 2;
-  }
-  // fp32-accumulate screened path: correct but measured slower than the exact path (57 vs 51.5 ms
-  // per 2000 queries), so it is opt-in
-  const char* want_screen = getenv("SS_SCORE_FP32_SCREEN");
-
   ScoreParams p{};
-  p.screen_ok = ix->weights_nonneg && want_screen && atoi(want_screen);
   p.sort_max = kSortMax;
+  p.owner_path = 1;
+  if (const char* env = getenv("SS_SCORE_OWNER")) p.owner_path = atoi(env);
   if (const char* env = getenv("SS_SCORE_SORT_MAX")) p.sort_max = std::min<uint32_t>(kSortMax, (uint32_t)atoi(env));
   p.meta32 = ix->meta32.p;
   p.tab[0] = view_of(ix->tab[0]);
@@ -1079,6 +1056,9 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   p.part_pr = ws.part_pr.p;
   p.part_count = ws.part_count.p;
   p.stats = ws.stats.p;
+  p.qthr = ws.qthr.p;
+  p.use_qthr = 1;
+  if (const char* env = getenv("SS_SCORE_QTHR")) p.use_qthr = atoi(env);
 
   p.narrow = ws.narrow.p;
   p.prefetch_meta = 0;  // measured: no effect (the finalize step is issue bound, not latency bound)
