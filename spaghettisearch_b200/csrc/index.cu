@@ -214,7 +214,7 @@ SS_API int ss_index_load(ss_engine* e, int table, uint64_t n_terms, uint64_t n_d
     return SS_ERR_INVALID;
   }
   tb.loaded = true;
-  ix->wcheck_valid = false;
+  ix->dense_valid = false;
   return SS_OK;
 }
 
@@ -271,7 +271,7 @@ SS_API int ss_term_weights(ss_engine* e, int table, double total_docs, const uin
   }
   tb.has_mag = true;
   ix->meta32_valid = false;
-  ix->wcheck_valid = false;
+  ix->dense_valid = false;
   if (out_w && P) SS_CUDA(cudaMemcpyAsync(out_w, tb.w.p, P * 4, cudaMemcpyDeviceToHost, st));
   if (out_mag && D) SS_CUDA(cudaMemcpyAsync(out_mag, tb.mag.p, D * 8, cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaStreamSynchronize(st));
@@ -294,7 +294,7 @@ SS_API int ss_set_doc_norms(ss_engine* e, int table, uint64_t n_docs, const doub
   SS_CUDA(cudaStreamSynchronize(e->stream));
   tb.has_mag = true;
   ix->meta32_valid = false;
-  ix->wcheck_valid = false;
+  ix->dense_valid = false;
   return SS_OK;
 }
 
@@ -306,7 +306,7 @@ SS_API int ss_set_pagerank(ss_engine* e, uint64_t n_docs, uint32_t n_topics, con
   SS_REQUIRE(ix, SS_ERR_OOM, "host allocation failed");
   ix->sqd_valid = false;
   ix->meta32_valid = false;
-  ix->wcheck_valid = false;
+  ix->dense_valid = false;
   if (!rank || n_docs == 0 || n_topics == 0) {
     ix->pr.reset();
     ix->T = 0;
@@ -329,7 +329,7 @@ SS_API int ss_use_pagerank(ss_engine* e) {
   SS_REQUIRE(ix, SS_ERR_OOM, "host allocation failed");
   ix->sqd_valid = false;
   ix->meta32_valid = false;
-  ix->wcheck_valid = false;
+  ix->dense_valid = false;
   uint64_t rows = 0;
   uint32_t topics = 0;
   SS_TRY(pagerank_export_device(e, &ix->pr, &rows, &topics));

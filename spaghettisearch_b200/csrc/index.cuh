@@ -41,9 +41,18 @@ struct IndexState {
   ss::DevBuf<float4> meta32;
   bool meta32_valid = false;
   int meta32_mode = -1;
-  // all weights finite and >= 0 (checked lazily by score.cu; enables the fp32 screened path)
-  bool wcheck_valid = false;
-  bool weights_nonneg = false;
+  // Impact vectors of the densest terms (score.cu): for each of the n_dense terms with the most
+  // postings, one fp16 value per doc = an upper bound of 100 * (0.38 w_title / |title| + 0.29 w_body /
+  // |body|) (0 = the doc has no posting of the term), plus zvec = upper bound of 33 * blend input.
+  // Rebuilt when weights, norms or blend inputs change.
+  bool dense_valid = false;     // uvec / dense_map match the current weights and norms
+  bool zvec_valid = false;      // zvec matches meta32
+  uint32_t n_dense = 0;
+  uint64_t d_pad = 0;           // padded doc count of one vector
+  ss::DevBuf<uint16_t> uvec;    // [n_dense][d_pad] fp16 bits
+  ss::DevBuf<uint16_t> zvec;    // [d_pad]
+  ss::DevBuf<uint8_t> dense_map;  // [V] dense slot of a term, 255 = none
+  uint64_t dense_map_V = 0;
   ss_score_stats stats{};
   // grow-only device workspace of ss_score_batch (cudaMalloc/cudaFree per batch would
   // synchronise the device and dominate small batches)

@@ -26,6 +26,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cuda_fp16.h>
+
 #include "index.cuh"
 
 namespace {
@@ -39,6 +41,9 @@ constexpr int kMaxPh = 32;     // phrase tokens per query handled in-kernel
 constexpr int kMaxLists = 2 * (kMaxKw + kMaxPh);
 constexpr int kBounds = 4096;   // sub-range boundary table entries per pass
 constexpr uint32_t kNoDoc = 0xFFFFFFFFu;
+constexpr int kDenseRange = 4096;  // docs per sub-range of the impact-vector path
+constexpr int kMaxDense = 254;     // dense slots (uint8 map, 255 = none)
+constexpr int kDensePadDocs = 2 * kDenseRange;
 
 struct TableView {
   const uint64_t* term_ptr;
@@ -75,6 +80,11 @@ struct ScoreParams {
   unsigned long long* stats;  // [0] postings scanned, [1] docs matched
   unsigned long long* qthr;   // [n_q] running per-query bound (score key), zeroed per batch
   int use_qthr;
+  // impact vectors of the densest terms (see IndexState)
+  const uint16_t* uvec;       // [n_dense][d_pad] fp16 bits, NULL = path disabled
+  const uint16_t* zvec;       // [d_pad]
+  const uint8_t* dense_map;   // [dense_map_V]
+  uint64_t d_pad, dense_map_V;
 };
 
 // Total order of results: FinalRank descending, ties by ascending doc id, NaN
@@ -123,6 +133,10 @@ struct Smem {
   float thr_f;  // fp32 lower bound of the score a doc needs: max(local k-th best, the query's running bound)
   unsigned long long gkey;  // the query's running bound (score key of some slab's k-th best), 0 = none
   float gthr_f;             // its score rounded down to fp32 (-inf when none)
+  uint8_t tok_dense[kMaxKw];   // dense slot of every keyword token (255 = sparse)
+  uint8_t dense_slots[kMaxKw]; // the dense tokens' slots, in token order
+  uint8_t sparse_toks[kMaxKw]; // indices of the sparse tokens
+  uint32_t n_dense_tok, n_sparse_tok;
 };
 
 // Union of the running top-k and the candidate buffer -> new running top-k by
@@ -538,6 +552,163 @@ __device__ void owner_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t s
   }
 }
 
+// ---- impact-vector path ----------------------------------------------------------------------
+// Keyword queries that contain one of the densest terms (>= 1/32 of the docs; 96 % of the
+// benchmark's postings belong to ~220 such terms).  Walking a 5M-posting list costs 8 B and ~150
+// thread instructions per posting in the accumulator path; here the term's whole contribution to
+// the SCREENING bound of a doc is one precomputed fp16 value (2 B, coalesced, no doc ids, no
+// atomics): U_t[d] >= 100 * (0.38 w_title/|title| + 0.29 w_body/|body|), rounded up, 0 = no
+// posting.  A sub-range of kDenseRange docs is streamed: bound(d) = blend_scale * Z[d] +
+// (sum of the dense tokens' U[d] + the sparse tokens' scattered fp32 impacts) / |q|, all terms
+// non-negative and rounded up, so bound(d) >= FinalRank(d).  Only docs whose bound reaches the
+// running threshold are evaluated exactly: their weights are looked up in the posting lists by
+// binary search and folded in query-token order -- the same fp64 sums, cosine and blend as the
+// other paths, so the top k is identical (tests/test_scoring_gpu.py compares the paths).
+__device__ __forceinline__ float half_bits_to_float(uint32_t h) {
+  return __half2float(__ushort_as_half((unsigned short)h));
+}
+
+__device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t slab_lo, uint64_t slab_hi, uint32_t n_kw,
+                          double qm, float qf_inv, float blend_scale, uint32_t k, unsigned long long& n_postings,
+                          unsigned long long& n_matched) {
+  constexpr int RD = kDenseRange;
+  float* sacc = reinterpret_cast<float*>(&s.acc[0][0]);            // [RD] sparse tokens' impact sums
+  uint16_t* surv = reinterpret_cast<uint16_t*>(&s.acc[1][0]);      // [RD] ring of surviving slots
+  uint32_t* dbits = reinterpret_cast<uint32_t*>(surv + RD);        // [RD / 32] presence from sparse tokens
+  const uint32_t tid = threadIdx.x, n_lists = 2 * n_kw;
+  const uint32_t nd = s.n_dense_tok, nsp = s.n_sparse_tok;
+  const uint32_t n_sub = (uint32_t)((slab_hi - slab_lo + RD - 1) / RD);
+  if (tid == 0) {
+    unsigned long long tot = 0;
+    for (uint32_t l = 0; l < n_lists; ++l) tot += s.len[l];
+    n_postings += tot;  // nominal: the posting lists this (query, slab) pair covers
+  }
+  // sparse tokens: posting offsets at every sub-range boundary
+  bool has_sparse = false;
+  for (uint32_t i = 0; i < nsp; ++i) has_sparse |= (s.len[2 * s.sparse_toks[i]] | s.len[2 * s.sparse_toks[i] + 1]) != 0;
+  if (has_sparse) {
+    for (uint32_t idx = tid; idx < 2 * nsp * (n_sub + 1); idx += kT) {
+      const uint32_t li = idx / (n_sub + 1), j = idx % (n_sub + 1);
+      const uint32_t l = 2 * s.sparse_toks[li >> 1] + (li & 1);
+      const uint64_t target = min(slab_hi, slab_lo + (uint64_t)j * RD);
+      s.bounds[idx] = s.len[l] ? (uint32_t)(lower_bound_doc(p.tab[l & 1].doc_ids, s.base[l], s.base[l] + s.len[l], target) - s.base[l]) : 0u;
+    }
+    for (uint32_t i = tid; i < RD; i += kT) sacc[i] = 0.0f;
+    for (uint32_t i = tid; i < RD / 32; i += kT) dbits[i] = 0;
+  }
+  __syncthreads();
+  uint32_t surv_done = s.n_list;
+  for (uint32_t sj = 0; sj < n_sub; ++sj) {
+    const uint64_t d0 = slab_lo + (uint64_t)sj * RD, d1 = min(slab_hi, d0 + RD);
+    bool any_sp = false;
+    if (has_sparse) {
+      for (uint32_t li = 0; li < 2 * nsp; ++li)
+        any_sp |= s.bounds[li * (n_sub + 1) + sj] != s.bounds[li * (n_sub + 1) + sj + 1];
+    }
+    if (any_sp) {
+      for (uint32_t li = 0; li < 2 * nsp; ++li) {
+        const uint32_t l = 2 * s.sparse_toks[li >> 1] + (li & 1);
+        const unsigned long long x0 = s.base[l] + s.bounds[li * (n_sub + 1) + sj];
+        const unsigned long long x1 = s.base[l] + s.bounds[li * (n_sub + 1) + sj + 1];
+        const TableView& tv = p.tab[l & 1];
+        for (unsigned long long x = x0 + tid; x < x1; x += kT) {
+          const uint32_t doc = tv.doc_ids[x];
+          const float w = tv.w[x];
+          const float4 m = p.meta32[doc];
+          float v = (l & 1) ? 29.0f * (w * m.y) : 38.0f * (w * m.x);
+          v = fmaxf(v, 0.0f) * 1.00001f;  // NaN -> 0: a NaN component counts as 0 in the reference too
+          const uint32_t slot = (uint32_t)(doc - d0);
+          atomicAdd(&sacc[slot], v);
+          atomicOr(&dbits[slot >> 5], 1u << (slot & 31));
+        }
+      }
+      __syncthreads();
+    }
+    // stream the sub-range: 8 consecutive docs per thread and step
+    const float thr_f = s.thr_f;
+    uint32_t my_matched = 0;
+#pragma unroll 1
+    for (uint32_t g0 = 0; g0 < RD; g0 += 8 * kT) {
+      const uint32_t slot0 = g0 + 8 * tid;
+      const uint64_t doc0 = d0 + slot0;
+      if (doc0 >= d1) continue;
+      float sum[8];
+      uint32_t present = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum[j] = 0.0f;
+      for (uint32_t i = 0; i < nd; ++i) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.uvec + (size_t)s.dense_slots[i] * p.d_pad + doc0));
+        const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t lo = uw[j] & 0xFFFFu, hi = uw[j] >> 16;
+          sum[2 * j] += half_bits_to_float(lo);
+          sum[2 * j + 1] += half_bits_to_float(hi);
+          present |= (lo ? 1u : 0u) << (2 * j);
+          present |= (hi ? 1u : 0u) << (2 * j + 1);
+        }
+      }
+      if (any_sp) {
+        present |= (dbits[slot0 >> 5] >> (slot0 & 31)) & 0xFFu;
+        const float4 a0 = *reinterpret_cast<const float4*>(sacc + slot0);
+        const float4 a1 = *reinterpret_cast<const float4*>(sacc + slot0 + 4);
+        sum[0] += a0.x; sum[1] += a0.y; sum[2] += a0.z; sum[3] += a0.w;
+        sum[4] += a1.x; sum[5] += a1.y; sum[6] += a1.z; sum[7] += a1.w;
+      }
+      if (doc0 + 8 > d1) present &= (1u << (uint32_t)(d1 - doc0)) - 1u;
+      if (!present) continue;
+      my_matched += __popc(present);
+      const uint4 zz = __ldg(reinterpret_cast<const uint4*>(p.zvec + doc0));
+      const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (!((present >> j) & 1u)) continue;
+        const float z = half_bits_to_float(j & 1 ? zw[j >> 1] >> 16 : zw[j >> 1] & 0xFFFFu);
+        const float a = blend_scale * z, b = qf_inv * sum[j];
+        if ((a + b) + (fabsf(a) + fabsf(b)) * 1e-4f + 1e-30f < thr_f) continue;  // NaN and +inf stay in
+        surv[atomicAdd(&s.n_list, 1u) & (RD - 1)] = (uint16_t)(slot0 + j);
+      }
+    }
+    n_matched += my_matched;
+    __syncthreads();
+    // clean the sparse scratch for the next sub-range (not read again before the next barrier)
+    if (any_sp) {
+      for (uint32_t i = tid; i < RD; i += kT) sacc[i] = 0.0f;
+      for (uint32_t i = tid; i < RD / 32; i += kT) dbits[i] = 0;
+    }
+    const uint32_t surv_end = s.n_list;
+    for (uint32_t r0 = surv_done; r0 != surv_end; r0 += min((uint32_t)kCand, surv_end - r0)) {
+      const uint32_t cnt = min((uint32_t)kCand, surv_end - r0);
+      for (uint32_t i = tid; i < cnt; i += kT) {
+        const uint32_t doc = (uint32_t)(d0 + surv[(r0 + i) & (RD - 1)]);
+        double tr = 0.0, br = 0.0;
+        bool first_t = true, first_b = true;
+        for (uint32_t l = 0; l < n_lists; ++l) {
+          const uint32_t len = s.len[l];
+          if (!len) continue;
+          const TableView& tv = p.tab[l & 1];
+          const unsigned long long b0 = s.base[l];
+          const unsigned long long at = lower_bound_doc(tv.doc_ids, b0, b0 + len, doc);
+          if (at == b0 + len || tv.doc_ids[at] != doc) continue;
+          const double w = (double)tv.w[at];
+          if (l & 1u) {
+            br = first_b ? w : __dadd_rn(br, w);
+            first_b = false;
+          } else {
+            tr = first_t ? w : __dadd_rn(tr, w);
+            first_t = false;
+          }
+        }
+        finish_exact(p, s, q, doc, tr, br, qm, k);
+      }
+      __syncthreads();
+      if (s.n_cand) merge_candidates(s, k);
+    }
+    surv_done = surv_end;
+    if (any_sp) __syncthreads();  // the scratch is clean before the next scatter
+  }
+}
+
 __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
@@ -572,6 +743,18 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
     s.gkey = g;
     s.gthr_f = (g == 0ull || isnan(gs)) ? -__int_as_float(0x7f800000) : __double2float_rd(gs);
     s.thr_f = s.gthr_f;
+  }
+  // which keyword tokens have an impact vector
+  if (tid == 0) {
+    uint32_t ndt = 0, nst = 0;
+    for (uint32_t i = 0; i < n_kw; ++i) {
+      const uint32_t term = p.kw_terms[kb + i];
+      const uint8_t slot = (p.uvec && term < p.dense_map_V) ? p.dense_map[term] : (uint8_t)255;
+      s.tok_dense[i] = slot;
+      if (slot != 255) s.dense_slots[ndt++] = slot; else s.sparse_toks[nst++] = (uint8_t)i;
+    }
+    s.n_dense_tok = ndt;
+    s.n_sparse_tok = nst;
   }
   // narrow every list to the slab
   for (uint32_t l = tid; l < n_lists; l += kT) {
@@ -610,6 +793,9 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
 
   if (work == 0) {
     // nothing of this query lives in this slab
+  } else if (n_ph == 0 && s.n_dense_tok > 0 && work > p.sort_max &&
+             2 * s.n_sparse_tok * ((slab_hi - slab_lo + kDenseRange - 1) / kDenseRange + 1) <= (uint64_t)kBounds) {
+    dtiv_path(p, s, q, slab_lo, slab_hi, n_kw, qm, qf_inv, blend_scale, k, n_postings, n_matched);
   } else if (work <= p.sort_max && n_ph == 0 && p.owner_path) {
     owner_path(p, s, q, slab_lo, n_kw, qm, qf_inv, blend_scale, k, n_postings, n_matched);
   } else if (work <= p.sort_max && p.slab_docs <= (1ull << 24)) {
@@ -873,6 +1059,59 @@ __global__ void k_meta32(const double* __restrict__ mag_t, const double* __restr
   out[d] = m;
 }
 
+// ---- impact vectors: build ---------------------------------------------------------------------
+// candidates: terms whose title + body postings reach min_df
+__global__ void k_dense_candidates(TableView t0, TableView t1, uint64_t V, uint64_t min_df, uint32_t cap,
+                                   uint32_t* __restrict__ n_out, uint32_t* __restrict__ out_term,
+                                   unsigned long long* __restrict__ out_df) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= V) return;
+  unsigned long long df = 0;
+  if (t0.term_ptr && t < t0.V) df += t0.term_ptr[t + 1] - t0.term_ptr[t];
+  if (t1.term_ptr && t < t1.V) df += t1.term_ptr[t + 1] - t1.term_ptr[t];
+  if (df < min_df || df == 0) return;
+  const uint32_t i = atomicAdd(n_out, 1u);
+  if (i < cap) {
+    out_term[i] = (uint32_t)t;
+    out_df[i] = df;
+  }
+}
+__global__ void k_dense_map(const uint32_t* __restrict__ terms, uint32_t n, uint8_t* __restrict__ map) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) map[terms[i]] = (uint8_t)i;
+}
+// One table's postings of the dense terms into the vectors: U[slot][doc] (+)= coef * w / norm, rounded up,
+// never 0 for a posting.  blockIdx.y = dense slot.  The two tables run one after the other (a table holds a
+// doc at most once per term, so there are no races).
+__global__ void k_dense_fill(TableView tv, int table, const uint32_t* __restrict__ terms, const float4* __restrict__ meta32,
+                             uint64_t d_pad, uint16_t* __restrict__ uvec) {
+  const uint32_t term = terms[blockIdx.y];
+  if (!tv.term_ptr || term >= tv.V) return;
+  const uint64_t a = tv.term_ptr[term], b = tv.term_ptr[term + 1];
+  uint16_t* u = uvec + (size_t)blockIdx.y * d_pad;
+  for (uint64_t x = a + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < b; x += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t doc = tv.doc_ids[x];
+    const float w = tv.w[x];
+    const float4 m = meta32[doc];
+    float v = table ? 29.0f * (w * m.y) : 38.0f * (w * m.x);
+    v = fmaxf(v, 0.0f) * 1.00001f;  // NaN -> 0 (a NaN component counts as 0, get_metadata.go:61-66)
+    const float old = __half2float(__ushort_as_half(u[doc]));
+    unsigned short h = __half_as_ushort(__float2half_ru(old + v * 1.00001f));
+    if (h == 0) h = 1;  // smallest positive value: "has a posting"
+    u[doc] = h;
+  }
+}
+__global__ void k_zvec(const float4* __restrict__ meta32, uint64_t D, uint64_t d_pad, uint16_t* __restrict__ zvec) {
+  const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= d_pad) return;
+  float z = 0.0f;
+  if (d < D) {
+    z = 33.0f * meta32[d].z;
+    z += fabsf(z) * 1e-5f;
+  }
+  zvec[d] = __half_as_ushort(__float2half_ru(z));
+}
+
 TableView view_of(const TableState& tb) {
   TableView v{};
   if (!tb.loaded) return v;
@@ -886,6 +1125,77 @@ TableView view_of(const TableState& tb) {
 }
 
 }  // namespace
+
+// Build (or refresh) the impact vectors; see IndexState.  Called with the engine lock held and meta32 fresh.
+static int build_dense_vectors(ss_engine* e, IndexState* ix, cudaStream_t st, uint32_t* launches) {
+  const uint64_t D = ix->D;
+  uint32_t frac = 32, max_dense = 224;
+  if (const char* env = getenv("SS_SCORE_DENSE_FRAC")) frac = (uint32_t)std::max(1, atoi(env));
+  if (const char* env = getenv("SS_SCORE_DENSE_MAX")) max_dense = (uint32_t)std::min(kMaxDense, std::max(0, atoi(env)));
+  const uint64_t d_pad = (D + kDenseRange - 1) / kDenseRange * kDenseRange + kDensePadDocs;
+  if (!ix->dense_valid) {
+    ix->n_dense = 0;
+    const uint64_t V = std::max(ix->tab[0].loaded ? ix->tab[0].V : 0, ix->tab[1].loaded ? ix->tab[1].V : 0);
+    if (V && max_dense) {
+      constexpr uint32_t cap = 4096;
+      ss::DevBuf<uint32_t> d_n, d_term;
+      ss::DevBuf<unsigned long long> d_df;
+      SS_TRY(d_n.alloc(1));
+      SS_TRY(d_term.alloc(cap));
+      SS_TRY(d_df.alloc(cap));
+      SS_CUDA(cudaMemsetAsync(d_n.p, 0, 4, st));
+      const uint64_t min_df = std::max<uint64_t>(1, D / frac);
+      k_dense_candidates<<<ss::div_up(V, 256), 256, 0, st>>>(view_of(ix->tab[0]), view_of(ix->tab[1]), V, min_df, cap,
+                                                           d_n.p, d_term.p, d_df.p);
+      uint32_t n = 0;
+      SS_CUDA(cudaMemcpyAsync(&n, d_n.p, 4, cudaMemcpyDeviceToHost, st));
+      SS_CUDA(cudaStreamSynchronize(st));
+      n = std::min(n, cap);
+      std::vector<uint32_t> terms(n);
+      std::vector<unsigned long long> dfs(n);
+      if (n) {
+        SS_CUDA(cudaMemcpy(terms.data(), d_term.p, n * 4, cudaMemcpyDeviceToHost));
+        SS_CUDA(cudaMemcpy(dfs.data(), d_df.p, n * 8, cudaMemcpyDeviceToHost));
+      }
+      std::vector<uint32_t> order(n);
+      for (uint32_t i = 0; i < n; ++i) order[i] = i;
+      std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        return dfs[a] != dfs[b] ? dfs[a] > dfs[b] : terms[a] < terms[b];
+      });
+      const uint32_t nd = std::min(n, max_dense);
+      std::vector<uint32_t> chosen(nd);
+      for (uint32_t i = 0; i < nd; ++i) chosen[i] = terms[order[i]];
+      if (nd) {
+        SS_TRY(ws_reserve(ix->uvec, (size_t)nd * d_pad));
+        SS_TRY(ws_reserve(ix->dense_map, V));
+        SS_CUDA(cudaMemsetAsync(ix->uvec.p, 0, (size_t)nd * d_pad * 2, st));
+        SS_CUDA(cudaMemsetAsync(ix->dense_map.p, 0xFF, V, st));
+        SS_CUDA(cudaMemcpyAsync(d_term.p, chosen.data(), nd * 4, cudaMemcpyHostToDevice, st));
+        k_dense_map<<<ss::div_up(nd, 256), 256, 0, st>>>(d_term.p, nd, ix->dense_map.p);
+        const dim3 grid(64, nd);
+        for (int tb = 1; tb >= 0; --tb)
+          if (ix->tab[tb].loaded)
+            k_dense_fill<<<grid, 256, 0, st>>>(view_of(ix->tab[tb]), tb, d_term.p, ix->meta32.p, d_pad, ix->uvec.p);
+        SS_CUDA(cudaStreamSynchronize(st));  // d_term goes out of scope
+        SS_CUDA(cudaGetLastError());
+        *launches += 4;
+      }
+      ix->n_dense = nd;
+      ix->dense_map_V = V;
+    }
+    ix->d_pad = d_pad;
+    ix->dense_valid = true;
+    ix->zvec_valid = false;
+  }
+  if (ix->n_dense && !ix->zvec_valid) {
+    SS_TRY(ws_reserve(ix->zvec, d_pad));
+    k_zvec<<<ss::div_up(d_pad, 256), 256, 0, st>>>(ix->meta32.p, D, d_pad, ix->zvec.p);
+    *launches += 1;
+    ix->zvec_valid = true;
+  }
+  (void)e;
+  return SS_OK;
+}
 
 extern "C" {
 
@@ -1025,8 +1335,13 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
       ++launches;
       ix->meta32_valid = true;
       ix->meta32_mode = mode;
+      ix->zvec_valid = false;
     }
   }
+  // impact vectors of the densest terms (SS_SCORE_DENSE=0 disables the path)
+  bool use_dense = true;
+  if (const char* env = getenv("SS_SCORE_DENSE")) use_dense = atoi(env) != 0;
+  if (use_dense && D) SS_TRY(build_dense_vectors(e, ix, st, &launches));
 
   ScoreParams p{};
   p.sort_max = kSortMax;
@@ -1057,6 +1372,13 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   p.part_count = ws.part_count.p;
   p.stats = ws.stats.p;
   p.qthr = ws.qthr.p;
+  if (use_dense && ix->dense_valid && ix->n_dense) {
+    p.uvec = ix->uvec.p;
+    p.zvec = ix->zvec.p;
+    p.dense_map = ix->dense_map.p;
+    p.d_pad = ix->d_pad;
+    p.dense_map_V = ix->dense_map_V;
+  }
   p.use_qthr = 1;
   if (const char* env = getenv("SS_SCORE_QTHR")) p.use_qthr = atoi(env);
 

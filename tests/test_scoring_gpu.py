@@ -152,6 +152,35 @@ def test_hot_terms_many_ties(engine, synth_index):
         assert_same_results(got, ref)
 
 
+@pytest.mark.parametrize("env", [
+    {},                                                   # default: impact vectors + owner path + running bound
+    {"SS_SCORE_DENSE": "0"},                              # accumulator paths only
+    {"SS_SCORE_SORT_MAX": "0"},                           # every slab with a dense token takes the impact-vector path
+    {"SS_SCORE_SORT_MAX": "0", "SS_SCORE_DENSE_MAX": "3"},   # 3 dense terms: mixed dense + scattered sparse tokens
+    {"SS_SCORE_SORT_MAX": "0", "SS_SCORE_DENSE_FRAC": "100000"},  # every term with a posting is "dense" (up to 224)
+    {"SS_SCORE_QTHR": "0", "SS_SCORE_OWNER": "0"},        # first-version sparse path, no cross-slab bound
+])
+def test_scoring_paths_agree_with_oracle(engine, synth_index, monkeypatch, env):
+    # The execution paths of ss_score_batch differ only in HOW they find the docs worth an exact
+    # evaluation; every one must return the oracle's top k (ids, order, scores).
+    s = synth_index
+    q = synth.queries(1200, s["V"], seed=48)
+    hot = queries_csr([[0], [1], [0, 1], [0, 5000], [3, 0, 3], [2, 7, 11, 300, 19000], [250], [250, 251, 252]])
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    probs = np.full(16, 1.0 / 16)
+    for pr, tp in ((None, None), (s["pr"], probs)):
+        engine.set_pagerank(pr)  # also drops the cached impact vectors, so the env settings take effect
+        for kw_ptr, kw in ((q.kw_ptr, q.kw_terms), (hot[0], hot[1])):
+            for k in (10, 50):
+                got = engine.score_batch(kw_ptr, kw, topic_probs=tp, k=k)
+                ref = O.score_batch(s["ot"], s["ob"], s["D"], s["tmag"], s["bmag"], pr, kw_ptr, kw, topic_probs=tp, k=k)
+                assert_same_results(got, ref)
+    for key in env:
+        monkeypatch.delenv(key)
+    engine.set_pagerank(None)
+
+
 def test_term_weights_not_idempotent(engine):
     # term_weighting.go:42-47 multiplies the stored weight in place: a second call weighs again
     V, D = 300, 800
