@@ -51,6 +51,7 @@ struct IndexState {
   uint64_t d_pad = 0;           // padded doc count of one vector
   ss::DevBuf<uint16_t> uvec;    // [n_dense][d_pad] fp16 bits
   ss::DevBuf<uint16_t> zvec;    // [d_pad]
+  ss::DevBuf<float> zblk;       // [d_pad / 4096] largest blend term per doc block
   ss::DevBuf<uint8_t> dense_map;  // [V] dense slot of a term, 255 = none
   uint64_t dense_map_V = 0;
   ss_score_stats stats{};

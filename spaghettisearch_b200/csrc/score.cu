@@ -83,6 +83,7 @@ struct ScoreParams {
   // impact vectors of the densest terms (see IndexState)
   const uint16_t* uvec;       // [n_dense][d_pad] fp16 bits, NULL = path disabled
   const uint16_t* zvec;       // [d_pad]
+  const float* zblk;          // [d_pad / kRange] largest blend term of a doc block
   const uint8_t* dense_map;   // [dense_map_V]
   uint64_t d_pad, dense_map_V;
 };
@@ -126,6 +127,7 @@ struct Smem {
   uint32_t cand_doc[kCand];
   uint32_t top_doc[2][kMaxK];
   uint32_t bits[kRange / 32];
+  uint32_t dbits[kDenseRange / 32];  // impact-vector path: docs with a sparse-token posting
   uint16_t mlist[kRange];  // slots of the sub-range's matched docs, in first-touch order
   uint32_t n_cand, n_ent, n_list, top_n, top_buf;
   unsigned long long thr_key, piv_key;
@@ -568,13 +570,63 @@ __device__ __forceinline__ float half_bits_to_float(uint32_t h) {
   return __half2float(__ushort_as_half((unsigned short)h));
 }
 
+// exact sums of one doc over the query's lists (slab ranges), weights folded in list = token order
+__device__ __forceinline__ void exact_sums(const ScoreParams& p, const Smem& s, uint32_t n_lists, uint32_t doc,
+                                           uint64_t slab_lo, uint64_t slab_docs, double& tr, double& br) {
+  tr = br = 0.0;
+  bool first_t = true, first_b = true;
+  for (uint32_t l = 0; l < n_lists; ++l) {
+    const uint32_t len = s.len[l];
+    if (!len) continue;
+    const uint32_t* __restrict__ docs = p.tab[l & 1].doc_ids + s.base[l];
+    // interpolation start (docs are spread over the slab), then gallop to bracket the doc, then bisect
+    uint32_t pos = (uint32_t)min((uint64_t)len - 1, (uint64_t)len * (doc - slab_lo) / slab_docs);
+    uint32_t lo, hi;  // invariant: docs[lo - 1] < doc (or lo == 0), docs[hi] >= doc (or hi == len)
+    if (docs[pos] < doc) {
+      lo = pos + 1;
+      uint32_t step = 16;
+      hi = lo;
+      while (true) {
+        hi = min(len, lo + step);
+        if (hi == len || docs[hi] >= doc) break;
+        lo = hi + 1;
+        step <<= 1;
+      }
+    } else {
+      hi = pos;
+      uint32_t step = 16;
+      lo = hi;
+      while (true) {
+        lo = hi > step ? hi - step : 0u;
+        if (lo == 0 || docs[lo - 1] < doc) break;
+        hi = lo - 1;
+        step <<= 1;
+      }
+    }
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (docs[mid] < doc) lo = mid + 1; else hi = mid;
+    }
+    if (lo == len || docs[lo] != doc) continue;
+    const double w = (double)p.tab[l & 1].w[s.base[l] + lo];
+    if (l & 1u) {
+      br = first_b ? w : __dadd_rn(br, w);
+      first_b = false;
+    } else {
+      tr = first_t ? w : __dadd_rn(tr, w);
+      first_t = false;
+    }
+  }
+}
+
 __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t slab_lo, uint64_t slab_hi, uint32_t n_kw,
                           double qm, float qf_inv, float blend_scale, uint32_t k, unsigned long long& n_postings,
                           unsigned long long& n_matched) {
   constexpr int RD = kDenseRange;
+  constexpr uint32_t kRing = 2 * RD;                               // survivor ring capacity
   float* sacc = reinterpret_cast<float*>(&s.acc[0][0]);            // [RD] sparse tokens' impact sums
-  uint16_t* surv = reinterpret_cast<uint16_t*>(&s.acc[1][0]);      // [RD] ring of surviving slots
-  uint32_t* dbits = reinterpret_cast<uint32_t*>(surv + RD);        // [RD / 32] presence from sparse tokens
+  uint16_t* surv = reinterpret_cast<uint16_t*>(&s.acc[1][0]);      // [kRing] slab-relative slots >> 0 of survivors
+  uint32_t* dbits = s.dbits;                                       // [RD / 32] presence from sparse tokens
   const uint32_t tid = threadIdx.x, n_lists = 2 * n_kw;
   const uint32_t nd = s.n_dense_tok, nsp = s.n_sparse_tok;
   const uint32_t n_sub = (uint32_t)((slab_hi - slab_lo + RD - 1) / RD);
@@ -597,9 +649,14 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
     for (uint32_t i = tid; i < RD / 32; i += kT) dbits[i] = 0;
   }
   __syncthreads();
+  // survivors carry (sub-range, slot) as a slab-relative doc offset in 16 bits when the slab allows it,
+  // else they are flushed every sub-range (flush_each)
+  const bool flush_each = (slab_hi - slab_lo) > 65536u;
   uint32_t surv_done = s.n_list;
+  uint32_t my_matched = 0;
   for (uint32_t sj = 0; sj < n_sub; ++sj) {
     const uint64_t d0 = slab_lo + (uint64_t)sj * RD, d1 = min(slab_hi, d0 + RD);
+    const uint32_t rel0 = flush_each ? 0u : (uint32_t)(d0 - slab_lo);
     bool any_sp = false;
     if (has_sparse) {
       for (uint32_t li = 0; li < 2 * nsp; ++li)
@@ -624,16 +681,22 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
       }
       __syncthreads();
     }
-    // stream the sub-range: 8 consecutive docs per thread and step
+    // stream the sub-range: 8 consecutive docs per thread and step.  A group whose best bound (largest
+    // impact sum, the block's largest blend term) stays below the threshold is dropped with one test.
     const float thr_f = s.thr_f;
-    uint32_t my_matched = 0;
+    float za;  // the sub-range may straddle three kRange-doc blocks of zblk
+    {
+      const float z0 = p.zblk[d0 / kRange], z1 = p.zblk[d0 / kRange + 1], z2 = p.zblk[d0 / kRange + 2];
+      float zm = z0 != z0 || z1 != z1 || z2 != z2 ? z0 + z1 + z2 : fmaxf(z0, fmaxf(z1, z2));
+      za = blend_scale * zm;
+    }
 #pragma unroll 1
     for (uint32_t g0 = 0; g0 < RD; g0 += 8 * kT) {
       const uint32_t slot0 = g0 + 8 * tid;
       const uint64_t doc0 = d0 + slot0;
       if (doc0 >= d1) continue;
       float sum[8];
-      uint32_t present = 0;
+      uint32_t nzw[4] = {0u, 0u, 0u, 0u};  // 0xFFFF per half-word: some dense token has a posting of that doc
 #pragma unroll
       for (int j = 0; j < 8; ++j) sum[j] = 0.0f;
       for (uint32_t i = 0; i < nd; ++i) {
@@ -641,23 +704,33 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
         const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint32_t lo = uw[j] & 0xFFFFu, hi = uw[j] >> 16;
-          sum[2 * j] += half_bits_to_float(lo);
-          sum[2 * j + 1] += half_bits_to_float(hi);
-          present |= (lo ? 1u : 0u) << (2 * j);
-          present |= (hi ? 1u : 0u) << (2 * j + 1);
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&uw[j]));
+          sum[2 * j] += f.x;
+          sum[2 * j + 1] += f.y;
+          nzw[j] |= __vcmpne2(uw[j], 0u);
         }
       }
+      uint32_t sp_bits = 0;
       if (any_sp) {
-        present |= (dbits[slot0 >> 5] >> (slot0 & 31)) & 0xFFu;
+        sp_bits = (dbits[slot0 >> 5] >> (slot0 & 31)) & 0xFFu;
         const float4 a0 = *reinterpret_cast<const float4*>(sacc + slot0);
         const float4 a1 = *reinterpret_cast<const float4*>(sacc + slot0 + 4);
         sum[0] += a0.x; sum[1] += a0.y; sum[2] += a0.z; sum[3] += a0.w;
         sum[4] += a1.x; sum[5] += a1.y; sum[6] += a1.z; sum[7] += a1.w;
       }
+      // present docs (dense posting or sparse posting), docs past the slab end masked out
+      uint32_t present = sp_bits;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) present |= ((nzw[j] & 1u) << (2 * j)) | (((nzw[j] >> 16) & 1u) << (2 * j + 1));
       if (doc0 + 8 > d1) present &= (1u << (uint32_t)(d1 - doc0)) - 1u;
-      if (!present) continue;
       my_matched += __popc(present);
+      if (!present) continue;
+      float gmax = fmaxf(fmaxf(fmaxf(sum[0], sum[1]), fmaxf(sum[2], sum[3])), fmaxf(fmaxf(sum[4], sum[5]), fmaxf(sum[6], sum[7])));
+      {
+        const float b = qf_inv * gmax;
+        // fmaxf drops NaNs: a NaN sum can only come from inf - inf, impossible here (all terms >= 0)
+        if ((za + b) + (fabsf(za) + fabsf(b)) * 1e-4f + 1e-30f < thr_f) continue;
+      }
       const uint4 zz = __ldg(reinterpret_cast<const uint4*>(p.zvec + doc0));
       const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
 #pragma unroll
@@ -666,47 +739,38 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
         const float z = half_bits_to_float(j & 1 ? zw[j >> 1] >> 16 : zw[j >> 1] & 0xFFFFu);
         const float a = blend_scale * z, b = qf_inv * sum[j];
         if ((a + b) + (fabsf(a) + fabsf(b)) * 1e-4f + 1e-30f < thr_f) continue;  // NaN and +inf stay in
-        surv[atomicAdd(&s.n_list, 1u) & (RD - 1)] = (uint16_t)(slot0 + j);
+        surv[atomicAdd(&s.n_list, 1u) & (kRing - 1)] = (uint16_t)(rel0 + slot0 + j);
       }
     }
-    n_matched += my_matched;
     __syncthreads();
     // clean the sparse scratch for the next sub-range (not read again before the next barrier)
     if (any_sp) {
       for (uint32_t i = tid; i < RD; i += kT) sacc[i] = 0.0f;
       for (uint32_t i = tid; i < RD / 32; i += kT) dbits[i] = 0;
     }
+    // Exact evaluation of the survivors stalls the block on a few threads' dependent lookups, so it
+    // is deferred until the slab ends, the ring could overflow, or no threshold exists yet.
     const uint32_t surv_end = s.n_list;
-    for (uint32_t r0 = surv_done; r0 != surv_end; r0 += min((uint32_t)kCand, surv_end - r0)) {
-      const uint32_t cnt = min((uint32_t)kCand, surv_end - r0);
-      for (uint32_t i = tid; i < cnt; i += kT) {
-        const uint32_t doc = (uint32_t)(d0 + surv[(r0 + i) & (RD - 1)]);
-        double tr = 0.0, br = 0.0;
-        bool first_t = true, first_b = true;
-        for (uint32_t l = 0; l < n_lists; ++l) {
-          const uint32_t len = s.len[l];
-          if (!len) continue;
-          const TableView& tv = p.tab[l & 1];
-          const unsigned long long b0 = s.base[l];
-          const unsigned long long at = lower_bound_doc(tv.doc_ids, b0, b0 + len, doc);
-          if (at == b0 + len || tv.doc_ids[at] != doc) continue;
-          const double w = (double)tv.w[at];
-          if (l & 1u) {
-            br = first_b ? w : __dadd_rn(br, w);
-            first_b = false;
-          } else {
-            tr = first_t ? w : __dadd_rn(tr, w);
-            first_t = false;
-          }
+    const bool flush = flush_each || sj + 1 == n_sub || surv_end - surv_done > (uint32_t)RD ||
+                       (surv_end != surv_done && thr_f == -__int_as_float(0x7f800000));
+    if (flush) {
+      const uint64_t rel_base = flush_each ? d0 : slab_lo;
+      for (uint32_t r0 = surv_done; r0 != surv_end; r0 += min((uint32_t)kCand, surv_end - r0)) {
+        const uint32_t cnt = min((uint32_t)kCand, surv_end - r0);
+        for (uint32_t i = tid; i < cnt; i += kT) {
+          const uint32_t doc = (uint32_t)(rel_base + surv[(r0 + i) & (kRing - 1)]);
+          double tr, br;
+          exact_sums(p, s, n_lists, doc, slab_lo, p.slab_docs, tr, br);
+          finish_exact(p, s, q, doc, tr, br, qm, k);
         }
-        finish_exact(p, s, q, doc, tr, br, qm, k);
+        __syncthreads();
+        if (s.n_cand) merge_candidates(s, k);
       }
-      __syncthreads();
-      if (s.n_cand) merge_candidates(s, k);
+      surv_done = surv_end;
     }
-    surv_done = surv_end;
     if (any_sp) __syncthreads();  // the scratch is clean before the next scatter
   }
+  n_matched += my_matched;
 }
 
 __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
@@ -1101,6 +1165,25 @@ __global__ void k_dense_fill(TableView tv, int table, const uint32_t* __restrict
     u[doc] = h;
   }
 }
+// largest 33 * blend input of every kRange-doc block (one CTA per block)
+__global__ void k_zblk(const float4* __restrict__ meta32, uint64_t D, float* __restrict__ zblk) {
+  __shared__ float sm[256];
+  const uint64_t d0 = (uint64_t)blockIdx.x * kRange;
+  float m = -__int_as_float(0x7f800000);
+  for (uint64_t d = d0 + threadIdx.x; d < d0 + kRange && d < D; d += blockDim.x) {
+    float z = 33.0f * meta32[d].z;
+    z += fabsf(z) * 1e-5f;
+    m = z > m || z != z ? z : m;  // a NaN blend input poisons the block: its groups are never dropped
+    if (z != z) break;
+  }
+  sm[threadIdx.x] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = sm[0];
+    for (int i = 1; i < 256; ++i) r = (sm[i] > r || sm[i] != sm[i]) && r == r ? sm[i] : r;
+    zblk[blockIdx.x] = r == -__int_as_float(0x7f800000) ? 0.0f : r;
+  }
+}
 __global__ void k_zvec(const float4* __restrict__ meta32, uint64_t D, uint64_t d_pad, uint16_t* __restrict__ zvec) {
   const uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= d_pad) return;
@@ -1189,8 +1272,10 @@ static int build_dense_vectors(ss_engine* e, IndexState* ix, cudaStream_t st, ui
   }
   if (ix->n_dense && !ix->zvec_valid) {
     SS_TRY(ws_reserve(ix->zvec, d_pad));
+    SS_TRY(ws_reserve(ix->zblk, d_pad / kRange));
     k_zvec<<<ss::div_up(d_pad, 256), 256, 0, st>>>(ix->meta32.p, D, d_pad, ix->zvec.p);
-    *launches += 1;
+    k_zblk<<<(unsigned)(d_pad / kRange), 256, 0, st>>>(ix->meta32.p, D, ix->zblk.p);
+    *launches += 2;
     ix->zvec_valid = true;
   }
   (void)e;
@@ -1253,7 +1338,10 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   n_slabs = std::max(n_slabs, (want_ctas + n_q - 1) / n_q);
   n_slabs = std::min<uint64_t>(n_slabs, n_sub);
   n_slabs = std::min<uint64_t>(n_slabs, std::max<uint64_t>(1, (uint64_t)kMergeMax / k));
-  const uint64_t sub_per_slab = (n_sub + n_slabs - 1) / n_slabs;
+  uint64_t sub_per_slab = (n_sub + n_slabs - 1) / n_slabs;
+  // the impact-vector path keeps survivors as 16-bit slab offsets: slabs of <= 65536 docs when the merge allows
+  if (sub_per_slab > 65536 / kRange && (n_sub + 65536 / kRange - 1) / (65536 / kRange) <= std::max<uint64_t>(1, (uint64_t)kMergeMax / k))
+    sub_per_slab = 65536 / kRange;
   n_slabs = (n_sub + sub_per_slab - 1) / sub_per_slab;
   SS_REQUIRE(n_q * n_slabs < 0x7FFFFFFFull, SS_ERR_INVALID, "ss_score_batch: batch too large; split it");
 
@@ -1375,6 +1463,7 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   if (use_dense && ix->dense_valid && ix->n_dense) {
     p.uvec = ix->uvec.p;
     p.zvec = ix->zvec.p;
+    p.zblk = ix->zblk.p;
     p.dense_map = ix->dense_map.p;
     p.d_pad = ix->d_pad;
     p.dense_map_V = ix->dense_map_V;
