@@ -139,6 +139,7 @@ struct Smem {
   uint8_t dense_slots[kMaxKw]; // the dense tokens' slots, in token order
   uint8_t sparse_toks[kMaxKw]; // indices of the sparse tokens
   uint32_t n_dense_tok, n_sparse_tok;
+  float zred[kT / 32];
 };
 
 // Union of the running top-k and the candidate buffer -> new running top-k by
@@ -648,7 +649,33 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
     for (uint32_t i = tid; i < RD; i += kT) sacc[i] = 0.0f;
     for (uint32_t i = tid; i < RD / 32; i += kT) dbits[i] = 0;
   }
+  // largest blend term of the slab (group-level rejection test): one zblk entry per thread, warp max,
+  // combined through shared memory; a NaN entry disables the rejection
+  {
+    const uint64_t b0 = slab_lo / kRange, nb = (slab_hi - slab_lo + kRange - 1) / kRange;
+    float zm = -__int_as_float(0x7f800000);
+    bool nan = false;
+    for (uint64_t b = tid; b < nb; b += kT) {
+      const float z = p.zblk[b0 + b];
+      nan |= z != z;
+      zm = fmaxf(zm, z);
+    }
+    for (int o = 16; o; o >>= 1) zm = fmaxf(zm, __shfl_xor_sync(0xFFFFFFFFu, zm, o));
+    nan = __any_sync(0xFFFFFFFFu, nan);
+    if ((tid & 31) == 0) s.zred[tid >> 5] = nan ? __int_as_float(0x7fc00000) : zm;
+  }
   __syncthreads();
+  float za;
+  {
+    float zm = s.zred[0];
+    bool nan = zm != zm;
+    for (int w = 1; w < kT / 32; ++w) {
+      const float z = s.zred[w];
+      nan |= z != z;
+      zm = fmaxf(zm, z);
+    }
+    za = nan ? __int_as_float(0x7fc00000) : blend_scale * zm;
+  }
   // survivors carry (sub-range, slot) as a slab-relative doc offset in 16 bits when the slab allows it,
   // else they are flushed every sub-range (flush_each)
   const bool flush_each = (slab_hi - slab_lo) > 65536u;
@@ -684,12 +711,6 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
     // stream the sub-range: 8 consecutive docs per thread and step.  A group whose best bound (largest
     // impact sum, the block's largest blend term) stays below the threshold is dropped with one test.
     const float thr_f = s.thr_f;
-    float za;  // the sub-range may straddle three kRange-doc blocks of zblk
-    {
-      const float z0 = p.zblk[d0 / kRange], z1 = p.zblk[d0 / kRange + 1], z2 = p.zblk[d0 / kRange + 2];
-      float zm = z0 != z0 || z1 != z1 || z2 != z2 ? z0 + z1 + z2 : fmaxf(z0, fmaxf(z1, z2));
-      za = blend_scale * zm;
-    }
 #pragma unroll 1
     for (uint32_t g0 = 0; g0 < RD; g0 += 8 * kT) {
       const uint32_t slot0 = g0 + 8 * tid;
