@@ -620,6 +620,92 @@ __device__ __forceinline__ void exact_sums(const ScoreParams& p, const Smem& s, 
   }
 }
 
+// Whole-slab stream of the impact-vector path for keyword queries whose tokens in this slab are all
+// dense (no scattered sparse impacts) once a threshold exists: no barriers inside, two 8-doc groups
+// per thread and step with all loads issued first.  Survivors go to the ring as 16-bit slab offsets;
+// returns false (uniformly, after a barrier) if the ring overflowed -- the caller then redoes the slab
+// sub-range by sub-range.  ND = number of dense tokens when it is 1 or 2 (vector bases in registers),
+// 0 = any.
+template <int ND>
+__device__ __forceinline__ bool dtiv_stream_slab(const ScoreParams& p, Smem& s, uint16_t* surv, uint32_t ring_mask,
+                                                 uint32_t surv_done, uint64_t slab_lo, uint64_t slab_hi, uint32_t nd,
+                                                 float za, float blend_scale, float qf_inv, float thr_f,
+                                                 uint32_t& my_matched) {
+  const uint32_t tid = threadIdx.x;
+  const uint32_t n_docs = (uint32_t)(slab_hi - slab_lo);
+  const uint16_t* __restrict__ base[ND ? ND : 1];
+#pragma unroll
+  for (int i = 0; i < (ND ? ND : 1); ++i) base[i] = p.uvec + (size_t)s.dense_slots[i] * p.d_pad + slab_lo;
+  const uint16_t* __restrict__ zv = p.zvec + slab_lo;
+  bool ovf = false;
+  auto process = [&](const float (&sum)[8], uint32_t off) {
+    uint32_t present = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) present |= (sum[j] > 0.0f ? 1u : 0u) << j;  // impacts are >= 0, > 0 for a posting
+    if (off + 8 > n_docs) present &= (1u << (n_docs - off)) - 1u;
+    if (!present) return;
+    my_matched += __popc(present);
+    const float gmax = fmaxf(fmaxf(fmaxf(sum[0], sum[1]), fmaxf(sum[2], sum[3])),
+                             fmaxf(fmaxf(sum[4], sum[5]), fmaxf(sum[6], sum[7])));
+    {
+      const float b = qf_inv * gmax;
+      if ((za + b) + (fabsf(za) + fabsf(b)) * 1e-4f + 1e-30f < thr_f) return;
+    }
+    const uint4 zz = __ldg(reinterpret_cast<const uint4*>(zv + off));
+    const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (!((present >> j) & 1u)) continue;
+      const float z = half_bits_to_float(j & 1 ? zw[j >> 1] >> 16 : zw[j >> 1] & 0xFFFFu);
+      const float a = blend_scale * z, b = qf_inv * sum[j];
+      if ((a + b) + (fabsf(a) + fabsf(b)) * 1e-4f + 1e-30f < thr_f) continue;  // NaN and +inf stay in
+      const uint32_t pos = atomicAdd(&s.n_list, 1u);
+      if (pos - surv_done > ring_mask) ovf = true; else surv[pos & ring_mask] = (uint16_t)(off + j);
+    }
+  };
+  auto add8 = [](float (&sum)[8], const uint4& u) {
+    const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&uw[j]));
+      sum[2 * j] += f.x;
+      sum[2 * j + 1] += f.y;
+    }
+  };
+#pragma unroll 1
+  for (uint32_t off = 8 * tid; off < n_docs; off += 16 * kT) {
+    const uint32_t off2 = off + 8 * kT;
+    const bool has2 = off2 < n_docs;
+    float sa[8], sb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sa[j] = sb[j] = 0.0f;
+    if (ND) {
+      uint4 ua[ND ? ND : 1], ub[ND ? ND : 1];
+#pragma unroll
+      for (int i = 0; i < (ND ? ND : 1); ++i) {
+        ua[i] = __ldg(reinterpret_cast<const uint4*>(base[i] + off));
+        ub[i] = has2 ? __ldg(reinterpret_cast<const uint4*>(base[i] + off2)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int i = 0; i < (ND ? ND : 1); ++i) {
+        add8(sa, ua[i]);
+        add8(sb, ub[i]);
+      }
+    } else {
+      for (uint32_t i = 0; i < nd; ++i) {
+        const uint16_t* b = p.uvec + (size_t)s.dense_slots[i] * p.d_pad + slab_lo;
+        const uint4 ua = __ldg(reinterpret_cast<const uint4*>(b + off));
+        const uint4 ub = has2 ? __ldg(reinterpret_cast<const uint4*>(b + off2)) : make_uint4(0u, 0u, 0u, 0u);
+        add8(sa, ua);
+        add8(sb, ub);
+      }
+    }
+    process(sa, off);
+    if (has2) process(sb, off2);
+  }
+  return !__syncthreads_or(ovf ? 1 : 0);
+}
+
 __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t slab_lo, uint64_t slab_hi, uint32_t n_kw,
                           double qm, float qf_inv, float blend_scale, uint32_t k, unsigned long long& n_postings,
                           unsigned long long& n_matched) {
@@ -681,6 +767,34 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
   const bool flush_each = (slab_hi - slab_lo) > 65536u;
   uint32_t surv_done = s.n_list;
   uint32_t my_matched = 0;
+  if (!has_sparse && !flush_each && s.thr_f != -__int_as_float(0x7f800000)) {
+    // every token of the slab is dense and a threshold exists: one barrier-free pass over the slab
+    const float thr_f = s.thr_f;
+    uint32_t cnt = 0;
+    bool ok;
+    if (nd == 1) ok = dtiv_stream_slab<1>(p, s, surv, kRing - 1, surv_done, slab_lo, slab_hi, nd, za, blend_scale, qf_inv, thr_f, cnt);
+    else if (nd == 2) ok = dtiv_stream_slab<2>(p, s, surv, kRing - 1, surv_done, slab_lo, slab_hi, nd, za, blend_scale, qf_inv, thr_f, cnt);
+    else ok = dtiv_stream_slab<0>(p, s, surv, kRing - 1, surv_done, slab_lo, slab_hi, nd, za, blend_scale, qf_inv, thr_f, cnt);
+    if (ok) {
+      n_matched += cnt;
+      const uint32_t surv_end = s.n_list;
+      for (uint32_t r0 = surv_done; r0 != surv_end; r0 += min((uint32_t)kCand, surv_end - r0)) {
+        const uint32_t n_round = min((uint32_t)kCand, surv_end - r0);
+        for (uint32_t i = tid; i < n_round; i += kT) {
+          const uint32_t doc = (uint32_t)(slab_lo + surv[(r0 + i) & (kRing - 1)]);
+          double tr, br;
+          exact_sums(p, s, n_lists, doc, slab_lo, p.slab_docs, tr, br);
+          finish_exact(p, s, q, doc, tr, br, qm, k);
+        }
+        __syncthreads();
+        if (s.n_cand) merge_candidates(s, k);
+      }
+      return;
+    }
+    // the survivor ring overflowed (masses of ties at the threshold): forget the pass, go sub-range by sub-range
+    if (tid == 0) s.n_list = surv_done;
+    __syncthreads();
+  }
   for (uint32_t sj = 0; sj < n_sub; ++sj) {
     const uint64_t d0 = slab_lo + (uint64_t)sj * RD, d1 = min(slab_hi, d0 + RD);
     const uint32_t rel0 = flush_each ? 0u : (uint32_t)(d0 - slab_lo);
