@@ -259,7 +259,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic("pagerank_sweep_dram_bytes"), "peak_source": peak_src,
-                         "kernel": "k_sweep_short + k_sweep_long (one sweep)",
+                         "kernel": "k_sweep_short32 + k_sweep_long (one sweep)",
                          "algorithmic_bytes_per_sweep": b_pr, "avg_sweep_ms": avg_sweep_s * 1e3,
                          "gather_model_bytes_per_sweep": b_pr + gather_bytes,
                          "gather_model_GBps": (b_pr + gather_bytes) / avg_sweep_s / 1e9,
@@ -336,6 +336,18 @@ def run_scoring(args, eng, ext, rank, world, local, threads, cores, peak, peak_s
     kernel_ms = max_over_ranks(kernel_ms)
     wall_s = max_over_ranks(wall_s)
     achieved = alg_bytes / (score_ms * 1e-3) / 1e9
+    # The same batch with the impact-vector path and the cross-slab bound switched off: every posting of
+    # every query list is walked (the "batched sparse gather" taken literally).  Reported beside the
+    # default so that the effect of the screening structures is visible; results are identical.
+    os.environ["SS_SCORE_DENSE"] = "0"
+    os.environ["SS_SCORE_QTHR"] = "0"
+    eng.score_batch(kw_ptr, kw, topic_probs=probs, k=TOP_K, out=outs)
+    s_walk = eng.score_stats()
+    del os.environ["SS_SCORE_DENSE"], os.environ["SS_SCORE_QTHR"]
+    walk_ms = max_over_ranks(s_walk.kernel_ms)
+    walk = {"value": Q / (walk_ms * 1e-3), "unit": "queries/s", "ms_per_step": walk_ms, "steps": 1,
+            "roofline_frac": s_walk.algorithmic_bytes / (s_walk.score_kernel_ms * 1e-3) / 1e9 / peak,
+            "what": "SS_SCORE_DENSE=0 SS_SCORE_QTHR=0: posting lists walked for every query, same results"}
     sc = {
         "metric": "scoring_queries_per_s", "value": Q * args.steps / (kernel_ms * 1e-3), "unit": "queries/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms / args.steps,
@@ -357,7 +369,12 @@ def run_scoring(args, eng, ext, rank, world, local, threads, cores, peak, peak_s
                      "traffic": ncu_traffic("score_dram_bytes"), "peak_source": peak_src, "kernel": "k_score",
                      "algorithmic_bytes_per_batch": alg_bytes // max(1, args.steps),
                      "postings_per_batch": postings // max(1, args.steps),
-                     "avg_kernel_ms": score_ms / max(1, args.steps)},
+                     "avg_kernel_ms": score_ms / max(1, args.steps),
+                     "note": "algorithmic bytes = 8 B per posting of every query list (+ per matched doc, per "
+                             "result), re-reads across queries counted (SURVEY.md 8(d)); the impact-vector path "
+                             "reads 2 B per doc and dense term instead of the lists, so frac is a rate against "
+                             "the nominal bytes, not the bytes moved"},
+        "walk_every_posting": walk,
     }
     if world > 1:
         sc["config"]["note"] = "per-shard top-k lists; cross-shard merge (ss_merge_topk) not in the timed region"

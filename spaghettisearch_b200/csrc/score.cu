@@ -1158,40 +1158,50 @@ __global__ void __launch_bounds__(kT) k_merge(uint32_t n_lists, uint32_t k, uint
                                               const double* __restrict__ in_pr, const uint32_t* __restrict__ in_count,
                                               uint32_t* __restrict__ out_doc, double* __restrict__ out_final,
                                               double* __restrict__ out_pr, uint32_t* __restrict__ out_count) {
+  // The valid entries are compacted first: with the per-query running bound most per-slab lists are
+  // empty or short, and ranking by counting is quadratic in the number of entries it is given.
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_raw);
   uint32_t* doc = reinterpret_cast<uint32_t*>(key + (size_t)n_lists * k);
+  uint32_t* from = doc + (size_t)n_lists * k;
   __shared__ uint32_t total;
   const uint32_t q = blockIdx.x, n = n_lists * k;
   if (threadIdx.x == 0) total = 0;
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < n; i += kT) {
-    const uint32_t l = i / k, j = i % k;
-    const size_t src = list_major ? ((size_t)l * n_q + q) * k + j : ((size_t)q * n_lists + l) * k + j;
-    const uint32_t cnt = in_count[list_major ? (size_t)l * n_q + q : (size_t)q * n_lists + l];
-    const bool ok = j < cnt && in_doc[src] != kNoDoc;
-    key[i] = ok ? score_key(in_final[src]) : 0ull;
-    doc[i] = ok ? in_doc[src] : kNoDoc;
-    if (ok) atomicAdd(&total, 1u);
-  }
   for (uint32_t j = threadIdx.x; j < k; j += kT) {
     out_doc[(size_t)q * k + j] = kNoDoc;
     out_final[(size_t)q * k + j] = 0.0;
     out_pr[(size_t)q * k + j] = 0.0;
   }
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < n; i += kT) {
-    if (doc[i] == kNoDoc) continue;
+  for (uint32_t l = threadIdx.x; l < n_lists; l += kT) {
+    const uint32_t cnt = min(k, in_count[list_major ? (size_t)l * n_q + q : (size_t)q * n_lists + l]);
+    for (uint32_t j = 0; j < cnt; ++j) {
+      const size_t src = list_major ? ((size_t)l * n_q + q) * k + j : ((size_t)q * n_lists + l) * k + j;
+      const uint32_t d = in_doc[src];
+      if (d == kNoDoc) continue;
+      const uint32_t at = atomicAdd(&total, 1u);
+      key[at] = score_key(in_final[src]);
+      doc[at] = d;
+      from[at] = l * k + j;
+    }
+  }
+  __syncthreads();
+  const uint32_t nv = total;
+  (void)n;
+  for (uint32_t i = threadIdx.x; i < nv; i += kT) {
+    const unsigned long long ki = key[i];
+    const uint32_t di = doc[i];
     uint32_t rank = 0;
-    for (uint32_t j = 0; j < n; ++j) rank += (doc[j] != kNoDoc && beats(key[j], doc[j], key[i], doc[i])) ? 1u : 0u;
+    for (uint32_t j = 0; j < nv; ++j) rank += beats(key[j], doc[j], ki, di) ? 1u : 0u;
     if (rank < k) {
-      const uint32_t l = i / k, jj = i % k;
+      const uint32_t l = from[i] / k, jj = from[i] % k;
       const size_t src = list_major ? ((size_t)l * n_q + q) * k + jj : ((size_t)q * n_lists + l) * k + jj;
-      out_doc[(size_t)q * k + rank] = doc[i];
+      out_doc[(size_t)q * k + rank] = di;
       out_final[(size_t)q * k + rank] = in_final[src];
       out_pr[(size_t)q * k + rank] = in_pr[src];
     }
   }
+  __syncthreads();
   if (threadIdx.x == 0) out_count[q] = min(total, k);
 }
 
@@ -1520,7 +1530,7 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
     for (auto& x : ws.ev)
       if (!x) SS_CUDA(cudaEventCreate(&x));
   SS_CUDA(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  SS_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeMax * 12));
+  SS_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeMax * 16));
 
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[0], st));
   SS_CUDA(cudaMemcpyAsync(ws.kw_ptr.p, kw_ptr, (n_q + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -1614,7 +1624,7 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[1], st));
   k_score<<<(unsigned)(n_q * n_slabs), kT, sizeof(Smem), st>>>(p);
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[2], st));
-  k_merge<<<(unsigned)n_q, kT, (size_t)n_slabs * k * 12, st>>>((uint32_t)n_slabs, k, (uint32_t)n_q, 0, ws.part_doc.p,
+  k_merge<<<(unsigned)n_q, kT, (size_t)n_slabs * k * 16, st>>>((uint32_t)n_slabs, k, (uint32_t)n_q, 0, ws.part_doc.p,
                                                               ws.part_final.p, ws.part_pr.p, ws.part_count.p,
                                                               ws.out_doc.p, ws.out_final.p, ws.out_pr.p,
                                                               ws.out_count.p);
@@ -1672,8 +1682,8 @@ SS_API int ss_merge_topk(ss_engine* e, uint32_t n_lists, uint64_t n_q, uint32_t 
   SS_CUDA(cudaMemcpyAsync(d_fin.p, finals, n * 8, cudaMemcpyHostToDevice, st));
   SS_CUDA(cudaMemcpyAsync(d_pr.p, prs, n * 8, cudaMemcpyHostToDevice, st));
   SS_CUDA(cudaMemcpyAsync(d_cnt.p, counts, (size_t)n_lists * n_q * 4, cudaMemcpyHostToDevice, st));
-  SS_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeMax * 12));
-  k_merge<<<(unsigned)n_q, kT, (size_t)n_lists * k * 12, st>>>(n_lists, k, (uint32_t)n_q, 1, d_doc.p, d_fin.p, d_pr.p,
+  SS_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeMax * 16));
+  k_merge<<<(unsigned)n_q, kT, (size_t)n_lists * k * 16, st>>>(n_lists, k, (uint32_t)n_q, 1, d_doc.p, d_fin.p, d_pr.p,
                                                               d_cnt.p, o_doc.p, o_fin.p, o_pr.p, o_cnt.p);
   SS_CUDA(cudaMemcpyAsync(out_doc, o_doc.p, n_q * k * 4, cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaMemcpyAsync(out_final, o_fin.p, n_q * k * 8, cudaMemcpyDeviceToHost, st));
