@@ -630,7 +630,9 @@ template <int ND>
 __device__ __forceinline__ bool dtiv_stream_slab(const ScoreParams& p, Smem& s, uint16_t* surv, uint32_t ring_mask,
                                                  uint32_t surv_done, uint64_t slab_lo, uint64_t slab_hi, uint32_t nd,
                                                  float za, float blend_scale, float qf_inv, float thr_f,
-                                                 uint32_t& my_matched) {
+                                                 const uint32_t* excl, uint32_t& my_matched) {
+  // excl: bitmap over the slab of docs that also have a sparse-token posting; those are scored by the
+  // caller (their bound needs the sparse impacts), so they are masked out here.  NULL = none.
   const uint32_t tid = threadIdx.x;
   const uint32_t n_docs = (uint32_t)(slab_hi - slab_lo);
   const uint16_t* __restrict__ base[ND ? ND : 1];
@@ -642,6 +644,7 @@ __device__ __forceinline__ bool dtiv_stream_slab(const ScoreParams& p, Smem& s, 
     uint32_t present = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) present |= (sum[j] > 0.0f ? 1u : 0u) << j;  // impacts are >= 0, > 0 for a posting
+    if (excl) present &= ~((excl[off >> 5] >> (off & 31)) & 0xFFu);
     if (off + 8 > n_docs) present &= (1u << (n_docs - off)) - 1u;
     if (!present) return;
     my_matched += __popc(present);
@@ -725,7 +728,14 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
   // sparse tokens: posting offsets at every sub-range boundary
   bool has_sparse = false;
   for (uint32_t i = 0; i < nsp; ++i) has_sparse |= (s.len[2 * s.sparse_toks[i]] | s.len[2 * s.sparse_toks[i] + 1]) != 0;
-  if (has_sparse) {
+  // whole-slab mode (below) applies when the sparse tokens have few postings here and a threshold exists
+  constexpr uint32_t kSparseStage = 2048;
+  const bool flush_each = (slab_hi - slab_lo) > 65536u;
+  uint32_t sp_total = 0;
+  if (has_sparse)
+    for (uint32_t i = 0; i < nsp; ++i) sp_total += s.len[2 * s.sparse_toks[i]] + s.len[2 * s.sparse_toks[i] + 1];
+  const bool whole_slab = !flush_each && sp_total <= kSparseStage && s.thr_f != -__int_as_float(0x7f800000);
+  auto setup_subranges = [&]() {  // sub-range mode: boundary table of the sparse lists, clean scratch
     for (uint32_t idx = tid; idx < 2 * nsp * (n_sub + 1); idx += kT) {
       const uint32_t li = idx / (n_sub + 1), j = idx % (n_sub + 1);
       const uint32_t l = 2 * s.sparse_toks[li >> 1] + (li & 1);
@@ -734,7 +744,8 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
     }
     for (uint32_t i = tid; i < RD; i += kT) sacc[i] = 0.0f;
     for (uint32_t i = tid; i < RD / 32; i += kT) dbits[i] = 0;
-  }
+  };
+  if (has_sparse && !whole_slab) setup_subranges();
   // largest blend term of the slab (group-level rejection test): one zblk entry per thread, warp max,
   // combined through shared memory; a NaN entry disables the rejection
   {
@@ -764,24 +775,97 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
   }
   // survivors carry (sub-range, slot) as a slab-relative doc offset in 16 bits when the slab allows it,
   // else they are flushed every sub-range (flush_each)
-  const bool flush_each = (slab_hi - slab_lo) > 65536u;
   uint32_t surv_done = s.n_list;
   uint32_t my_matched = 0;
-  if (!has_sparse && !flush_each && s.thr_f != -__int_as_float(0x7f800000)) {
-    // every token of the slab is dense and a threshold exists: one barrier-free pass over the slab
+  // Whole-slab mode: every token of the slab is dense, or the sparse tokens have few postings here.
+  if (whole_slab) {
     const float thr_f = s.thr_f;
+    // mixed layout: acc[0] = staged sparse postings (slab offset, impact), acc[1] = survivor ring (4096) + bitmap
+    uint32_t* soff = reinterpret_cast<uint32_t*>(&s.acc[0][0]);
+    float* simp = reinterpret_cast<float*>(soff + kSparseStage);
+    uint32_t* excl = reinterpret_cast<uint32_t*>(surv + RD);  // [65536 / 32] words = 8 KB
+    const uint32_t ring_mask = has_sparse ? (uint32_t)RD - 1u : kRing - 1u;
+    if (has_sparse) {
+      __syncthreads();  // the sparse scratch set up above (sacc / bounds) is not used in this mode
+      for (uint32_t i = tid; i < 65536 / 32; i += kT) excl[i] = 0;
+      if (tid == 0) {
+        uint32_t run = 0;
+        for (uint32_t li = 0; li < 2 * nsp; ++li) {
+          s.bounds[li] = run;
+          run += s.len[2 * s.sparse_toks[li >> 1] + (li & 1)];
+        }
+        s.bounds[2 * nsp] = run;
+      }
+      __syncthreads();
+      for (uint32_t li = 0; li < 2 * nsp; ++li) {
+        const uint32_t l = 2 * s.sparse_toks[li >> 1] + (li & 1), len = s.len[l];
+        const TableView& tv = p.tab[l & 1];
+        for (uint32_t i = tid; i < len; i += kT) {
+          const uint32_t doc = tv.doc_ids[s.base[l] + i];
+          const float w = tv.w[s.base[l] + i];
+          const float4 m = p.meta32[doc];
+          float v = (l & 1) ? 29.0f * (w * m.y) : 38.0f * (w * m.x);
+          v = fmaxf(v, 0.0f) * 1.00001f;
+          const uint32_t off = (uint32_t)(doc - slab_lo);
+          soff[s.bounds[li] + i] = off;
+          simp[s.bounds[li] + i] = v;
+          atomicOr(&excl[off >> 5], 1u << (off & 31));
+        }
+      }
+      __syncthreads();
+    }
     uint32_t cnt = 0;
+    bool ovf_forced = false;
+    if (has_sparse) {
+      // docs with a sparse posting: the first sparse list that holds the doc owns it and bounds it with the
+      // doc's sparse impacts plus its entries of the dense vectors
+      auto find = [&](uint32_t lj, uint32_t off) -> uint32_t {
+        uint32_t lo = s.bounds[lj], hi = s.bounds[lj + 1];
+        const uint32_t end = hi;
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (soff[mid] < off) lo = mid + 1; else hi = mid;
+        }
+        return (lo < end && soff[lo] == off) ? lo : kNoDoc;
+      };
+      for (uint32_t idx = tid; idx < sp_total; idx += kT) {
+        uint32_t lo = 0, hi = 2 * nsp;  // last li with bounds[li] <= idx
+        while (hi - lo > 1) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (s.bounds[mid] <= idx) lo = mid; else hi = mid;
+        }
+        const uint32_t li = lo, off = soff[idx];
+        bool owner = true;
+        for (uint32_t j = 0; j < li && owner; ++j) owner = find(j, off) == kNoDoc;
+        if (!owner) continue;
+        ++cnt;
+        float sum = simp[idx];
+        for (uint32_t j = li + 1; j < 2 * nsp; ++j) {
+          const uint32_t at = find(j, off);
+          if (at != kNoDoc) sum += simp[at];
+        }
+        for (uint32_t i = 0; i < nd; ++i)
+          sum += half_bits_to_float(p.uvec[(size_t)s.dense_slots[i] * p.d_pad + slab_lo + off]);
+        const float z = half_bits_to_float(p.zvec[slab_lo + off]);
+        const float a = blend_scale * z, b = qf_inv * sum;
+        if ((a + b) + (fabsf(a) + fabsf(b)) * 1e-4f + 1e-30f < thr_f) continue;
+        const uint32_t pos = atomicAdd(&s.n_list, 1u);
+        if (pos - surv_done > ring_mask) ovf_forced = true; else surv[pos & ring_mask] = (uint16_t)off;
+      }
+    }
+    const uint32_t* ex = has_sparse ? excl : nullptr;
     bool ok;
-    if (nd == 1) ok = dtiv_stream_slab<1>(p, s, surv, kRing - 1, surv_done, slab_lo, slab_hi, nd, za, blend_scale, qf_inv, thr_f, cnt);
-    else if (nd == 2) ok = dtiv_stream_slab<2>(p, s, surv, kRing - 1, surv_done, slab_lo, slab_hi, nd, za, blend_scale, qf_inv, thr_f, cnt);
-    else ok = dtiv_stream_slab<0>(p, s, surv, kRing - 1, surv_done, slab_lo, slab_hi, nd, za, blend_scale, qf_inv, thr_f, cnt);
+    if (nd == 1) ok = dtiv_stream_slab<1>(p, s, surv, ring_mask, surv_done, slab_lo, slab_hi, nd, za, blend_scale, qf_inv, thr_f, ex, cnt);
+    else if (nd == 2) ok = dtiv_stream_slab<2>(p, s, surv, ring_mask, surv_done, slab_lo, slab_hi, nd, za, blend_scale, qf_inv, thr_f, ex, cnt);
+    else ok = dtiv_stream_slab<0>(p, s, surv, ring_mask, surv_done, slab_lo, slab_hi, nd, za, blend_scale, qf_inv, thr_f, ex, cnt);
+    ok = !__syncthreads_or(ovf_forced ? 1 : 0) && ok;
     if (ok) {
       n_matched += cnt;
       const uint32_t surv_end = s.n_list;
       for (uint32_t r0 = surv_done; r0 != surv_end; r0 += min((uint32_t)kCand, surv_end - r0)) {
         const uint32_t n_round = min((uint32_t)kCand, surv_end - r0);
         for (uint32_t i = tid; i < n_round; i += kT) {
-          const uint32_t doc = (uint32_t)(slab_lo + surv[(r0 + i) & (kRing - 1)]);
+          const uint32_t doc = (uint32_t)(slab_lo + surv[(r0 + i) & ring_mask]);
           double tr, br;
           exact_sums(p, s, n_lists, doc, slab_lo, p.slab_docs, tr, br);
           finish_exact(p, s, q, doc, tr, br, qm, k);
@@ -793,6 +877,7 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
     }
     // the survivor ring overflowed (masses of ties at the threshold): forget the pass, go sub-range by sub-range
     if (tid == 0) s.n_list = surv_done;
+    if (has_sparse) setup_subranges();  // the staged postings used the sub-range scratch
     __syncthreads();
   }
   for (uint32_t sj = 0; sj < n_sub; ++sj) {
