@@ -62,6 +62,7 @@ struct IndexState {
     ss::DevBuf<uint32_t> kw, ph, part_doc, part_count, out_doc, out_count, narrow;
     ss::DevBuf<double> probs, part_final, part_pr, out_final, out_pr, zero_mag;
     ss::DevBuf<unsigned long long> stats, qthr;
+    ss::DevBuf<uint8_t> group_len;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     ~Workspace() {
       for (auto& e : ev)

@@ -86,6 +86,9 @@ struct ScoreParams {
   const float* zblk;          // [d_pad / kRange] largest blend term of a doc block
   const uint8_t* dense_map;   // [dense_map_V]
   uint64_t d_pad, dense_map_V;
+  // slab groups (k_plan): group_len[q][slab] = number of consecutive slabs the CTA of (q, slab) scores as
+  // one range, 0 = the slab belongs to an earlier CTA's group (that CTA exits at once)
+  const uint8_t* group_len;
 };
 
 // Total order of results: FinalRank descending, ties by ascending doc id, NaN
@@ -997,6 +1000,8 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   const uint32_t q = blockIdx.x % p.n_q, slab = blockIdx.x / p.n_q;  // slab-major launch order
+  const uint32_t glen = p.group_len[(size_t)q * p.n_slabs + slab];
+  if (glen == 0) return;  // scored by the CTA that leads this slab's group (its part_count stays 0)
   const uint32_t tid = threadIdx.x;
   const uint64_t kb = p.kw_ptr[q], ke = p.kw_ptr[q + 1];
   const uint64_t pb = p.ph_ptr ? p.ph_ptr[q] : 0, pe = p.ph_ptr ? p.ph_ptr[q + 1] : 0;
@@ -1006,7 +1011,7 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
   if (n_ph > kMaxPh) n_ph = 0;                   // host rejects 33..256; >256 can never match (uint8 TermPos)
   const uint32_t n_tok = n_kw + n_ph, n_lists = 2 * n_tok;
   const uint64_t slab_lo = (uint64_t)slab * p.slab_docs;
-  const uint64_t slab_hi = min(p.D, slab_lo + p.slab_docs);
+  const uint64_t slab_hi = min(p.D, slab_lo + (uint64_t)glen * p.slab_docs);
   const uint32_t k = p.k;
 
   if (tid == 0) {
@@ -1049,7 +1054,7 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
     if (tv.term_ptr && term < tv.V) a = tv.term_ptr[term];  // unknown term => empty row (main_retrieve.go:193,218)
     // slab boundaries of every list were located once for the whole batch (k_narrow)
     const uint32_t* nar = p.narrow + ((size_t)2 * (kb + pb) + l) * (p.n_slabs + 1) + slab;
-    const uint32_t o0 = nar[0], o1 = nar[1];
+    const uint32_t o0 = nar[0], o1 = nar[glen];
     s.base[l] = a + o0;
     s.len[l] = o1 - o0;
   }
@@ -1082,7 +1087,7 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
     dtiv_path(p, s, q, slab_lo, slab_hi, n_kw, qm, qf_inv, blend_scale, k, n_postings, n_matched);
   } else if (work <= p.sort_max && n_ph == 0 && p.owner_path) {
     owner_path(p, s, q, slab_lo, n_kw, qm, qf_inv, blend_scale, k, n_postings, n_matched);
-  } else if (work <= p.sort_max && p.slab_docs <= (1ull << 24)) {
+  } else if (work <= p.sort_max && slab_hi - slab_lo <= (1ull << 24)) {
     sort_path(p, s, q, slab_lo, n_kw, n_ph, qm, qf_inv, blend_scale, k, n_postings, n_matched);
   } else {
   for (uint32_t i = tid; i < kRange; i += kT) {
@@ -1288,6 +1293,39 @@ __global__ void __launch_bounds__(kT) k_merge(uint32_t n_lists, uint32_t k, uint
   }
   __syncthreads();
   if (threadIdx.x == 0) out_count[q] = min(total, k);
+}
+
+// Slab groups of every query: consecutive slabs are merged while their postings (all lists of the query)
+// stay within merge_max, so that a query with short lists costs a few CTAs instead of one nearly empty
+// CTA per slab (each pays the same prologue, barriers and output writes).  Merged groups are small enough
+// for the sparse paths, which do not depend on the width of the doc range.
+__global__ void k_plan(ScoreParams p, uint32_t merge_max, uint8_t* __restrict__ group_len) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= p.n_q) return;
+  const uint64_t kb = p.kw_ptr[q], pb = p.ph_ptr ? p.ph_ptr[q] : 0;
+  const uint32_t n_lists = 2 * (uint32_t)((p.kw_ptr[q + 1] - kb) + (p.ph_ptr ? p.ph_ptr[q + 1] - pb : 0));
+  const uint32_t per = p.n_slabs + 1;
+  const uint32_t* nar = p.narrow + (size_t)2 * (kb + pb) * per;
+  auto work = [&](uint32_t sl) {
+    unsigned long long w = 0;
+    for (uint32_t l = 0; l < n_lists; ++l) w += nar[(size_t)l * per + sl + 1] - nar[(size_t)l * per + sl];
+    return w;
+  };
+  uint8_t* out = group_len + (size_t)q * p.n_slabs;
+  uint32_t sl = 0;
+  while (sl < p.n_slabs) {
+    unsigned long long w = work(sl);
+    uint32_t len = 1;
+    while (w <= merge_max && sl + len < p.n_slabs && len < 255) {
+      const unsigned long long w2 = work(sl + len);
+      if (w + w2 > merge_max) break;
+      w += w2;
+      ++len;
+    }
+    out[sl] = (uint8_t)len;
+    for (uint32_t i = 1; i < len; ++i) out[sl + i] = 0;
+    sl += len;
+  }
 }
 
 // Slab boundaries of every posting list of the batch: narrow[list][j] = offset, inside the
@@ -1706,6 +1744,16 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   if (const char* env = getenv("SS_SCORE_PREFETCH")) p.prefetch_meta = atoi(env);
   if (n_narrow) k_narrow<<<ss::div_up(n_narrow, 256), 256, 0, st>>>(p, ws.narrow.p, n_narrow);
   ++launches;
+  {
+    uint32_t merge_max = 3072;  // <= sort_max: merged groups take the sparse paths
+    if (const char* env = getenv("SS_SCORE_MERGE_MAX")) merge_max = (uint32_t)std::max(0, atoi(env));
+    merge_max = std::min(merge_max, p.sort_max);
+    SS_TRY(ws_reserve(ws.group_len, n_q * n_slabs));
+    SS_CUDA(cudaMemsetAsync(ws.part_count.p, 0, n_q * n_slabs * 4, st));
+    k_plan<<<ss::div_up(n_q, 128), 128, 0, st>>>(p, merge_max, ws.group_len.p);
+    p.group_len = ws.group_len.p;
+    ++launches;
+  }
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[1], st));
   k_score<<<(unsigned)(n_q * n_slabs), kT, sizeof(Smem), st>>>(p);
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[2], st));
