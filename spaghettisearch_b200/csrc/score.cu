@@ -870,7 +870,7 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
         for (uint32_t i = tid; i < n_round; i += kT) {
           const uint32_t doc = (uint32_t)(slab_lo + surv[(r0 + i) & ring_mask]);
           double tr, br;
-          exact_sums(p, s, n_lists, doc, slab_lo, p.slab_docs, tr, br);
+          exact_sums(p, s, n_lists, doc, slab_lo, slab_hi - slab_lo, tr, br);
           finish_exact(p, s, q, doc, tr, br, qm, k);
         }
         __syncthreads();
@@ -983,7 +983,7 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
         for (uint32_t i = tid; i < cnt; i += kT) {
           const uint32_t doc = (uint32_t)(rel_base + surv[(r0 + i) & (kRing - 1)]);
           double tr, br;
-          exact_sums(p, s, n_lists, doc, slab_lo, p.slab_docs, tr, br);
+          exact_sums(p, s, n_lists, doc, slab_lo, slab_hi - slab_lo, tr, br);
           finish_exact(p, s, q, doc, tr, br, qm, k);
         }
         __syncthreads();
@@ -1311,10 +1311,29 @@ __global__ void k_plan(ScoreParams p, uint32_t merge_max, uint8_t* __restrict__ 
     for (uint32_t l = 0; l < n_lists; ++l) w += nar[(size_t)l * per + sl + 1] - nar[(size_t)l * per + sl];
     return w;
   };
+  // keyword queries with a dense term: the impact-vector path streams up to 65536 docs per CTA
+  bool dense_q = false;
+  if (p.uvec && !(p.ph_ptr && p.ph_ptr[q + 1] > pb))
+    for (uint64_t i = kb; i < p.kw_ptr[q + 1] && !dense_q; ++i) {
+      const uint32_t term = p.kw_terms[i];
+      dense_q = term < p.dense_map_V && p.dense_map[term] != 255;
+    }
+  const uint32_t dense_len = dense_q ? (uint32_t)max((uint64_t)1, min((uint64_t)255, 65536 / p.slab_docs)) : 1u;
   uint8_t* out = group_len + (size_t)q * p.n_slabs;
   uint32_t sl = 0;
   while (sl < p.n_slabs) {
     unsigned long long w = work(sl);
+    if (dense_len > 1) {
+      const uint32_t len = min(dense_len, p.n_slabs - sl);
+      unsigned long long wg = w;
+      for (uint32_t i = 1; i < len; ++i) wg += work(sl + i);
+      if (wg > p.sort_max) {
+        out[sl] = (uint8_t)len;
+        for (uint32_t i = 1; i < len; ++i) out[sl + i] = 0;
+        sl += len;
+        continue;
+      }
+    }
     uint32_t len = 1;
     while (w <= merge_max && sl + len < p.n_slabs && len < 255) {
       const unsigned long long w2 = work(sl + len);
@@ -1608,8 +1627,18 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   n_slabs = std::min<uint64_t>(n_slabs, std::max<uint64_t>(1, (uint64_t)kMergeMax / k));
   uint64_t sub_per_slab = (n_sub + n_slabs - 1) / n_slabs;
   // the impact-vector path keeps survivors as 16-bit slab offsets: slabs of <= 65536 docs when the merge allows
-  if (sub_per_slab > 65536 / kRange && (n_sub + 65536 / kRange - 1) / (65536 / kRange) <= std::max<uint64_t>(1, (uint64_t)kMergeMax / k))
-    sub_per_slab = 65536 / kRange;
+  // (with smaller slabs k_plan merges them back into 65536-doc ranges for that path).  Measured: 32768-doc
+  // slabs help queries with several mid-frequency lists but cost more than that elsewhere (216K vs 206K
+  // queries/s on the benchmark mix), so 65536 is the default; SS_SCORE_SLAB_DOCS overrides.
+  uint64_t slab_target = 65536;
+  if (const char* env = getenv("SS_SCORE_SLAB_DOCS")) slab_target = std::max<uint64_t>(kRange, strtoull(env, nullptr, 10));
+  for (uint64_t t : {slab_target, (uint64_t)65536}) {
+    const uint64_t spt = std::max<uint64_t>(1, t / kRange);
+    if (sub_per_slab > spt && (n_sub + spt - 1) / spt <= std::max<uint64_t>(1, (uint64_t)kMergeMax / k)) {
+      sub_per_slab = spt;
+      break;
+    }
+  }
   n_slabs = (n_sub + sub_per_slab - 1) / sub_per_slab;
   SS_REQUIRE(n_q * n_slabs < 0x7FFFFFFFull, SS_ERR_INVALID, "ss_score_batch: batch too large; split it");
 
