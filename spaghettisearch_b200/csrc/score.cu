@@ -574,52 +574,76 @@ __device__ __forceinline__ float half_bits_to_float(uint32_t h) {
   return __half2float(__ushort_as_half((unsigned short)h));
 }
 
-// exact sums of one doc over the query's lists (slab ranges), weights folded in list = token order
-__device__ __forceinline__ void exact_sums(const ScoreParams& p, const Smem& s, uint32_t n_lists, uint32_t doc,
-                                           uint64_t slab_lo, uint64_t slab_docs, double& tr, double& br) {
-  tr = br = 0.0;
-  bool first_t = true, first_b = true;
-  for (uint32_t l = 0; l < n_lists; ++l) {
-    const uint32_t len = s.len[l];
-    if (!len) continue;
-    const uint32_t* __restrict__ docs = p.tab[l & 1].doc_ids + s.base[l];
-    // interpolation start (docs are spread over the slab), then gallop to bracket the doc, then bisect
-    uint32_t pos = (uint32_t)min((uint64_t)len - 1, (uint64_t)len * (doc - slab_lo) / slab_docs);
-    uint32_t lo, hi;  // invariant: docs[lo - 1] < doc (or lo == 0), docs[hi] >= doc (or hi == len)
-    if (docs[pos] < doc) {
-      lo = pos + 1;
-      uint32_t step = 16;
-      hi = lo;
-      while (true) {
-        hi = min(len, lo + step);
-        if (hi == len || docs[hi] >= doc) break;
-        lo = hi + 1;
-        step <<= 1;
+// The doc's weight in list l of the query (slab range), if it has one: interpolation start (docs are
+// spread over the slab), gallop to bracket the doc, bisect.
+__device__ __forceinline__ bool find_in_list(const ScoreParams& p, const Smem& s, uint32_t l, uint32_t doc,
+                                             uint64_t slab_lo, uint64_t slab_docs, float& w_out) {
+  const uint32_t len = s.len[l];
+  if (!len) return false;
+  const uint32_t* __restrict__ docs = p.tab[l & 1].doc_ids + s.base[l];
+  uint32_t pos = (uint32_t)min((uint64_t)len - 1, (uint64_t)len * (doc - slab_lo) / slab_docs);
+  uint32_t lo, hi;  // invariant: docs[lo - 1] < doc (or lo == 0), docs[hi] >= doc (or hi == len)
+  if (docs[pos] < doc) {
+    lo = pos + 1;
+    uint32_t step = 16;
+    while (true) {
+      hi = min(len, lo + step);
+      if (hi == len || docs[hi] >= doc) break;
+      lo = hi + 1;
+      step <<= 1;
+    }
+  } else {
+    hi = pos;
+    uint32_t step = 16;
+    while (true) {
+      lo = hi > step ? hi - step : 0u;
+      if (lo == 0 || docs[lo - 1] < doc) break;
+      hi = lo - 1;
+      step <<= 1;
+    }
+  }
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (docs[mid] < doc) lo = mid + 1; else hi = mid;
+  }
+  if (lo == len || docs[lo] != doc) return false;
+  w_out = p.tab[l & 1].w[s.base[l] + lo];
+  return true;
+}
+
+// Exact evaluation of n survivors (slab offsets in the ring from position r0): four lanes per doc look it
+// up in four lists at a time, the weights are folded in list (= query-token) order -- the same fp64 sums
+// as the accumulator paths -- and the group's first lane finishes the doc.  Every thread of the CTA calls.
+__device__ __forceinline__ void evaluate_survivors(const ScoreParams& p, Smem& s, uint32_t q, const uint16_t* surv,
+                                                   uint32_t ring_mask, uint32_t r0, uint32_t n, uint64_t rel_base,
+                                                   uint32_t n_lists, uint64_t slab_lo, uint64_t slab_docs, double qm,
+                                                   uint32_t k) {
+  const uint32_t sub = threadIdx.x >> 2, gl = threadIdx.x & 3;
+  for (uint32_t base = 0; base < n; base += kT / 4) {
+    const uint32_t i = base + sub;
+    const bool active = i < n;
+    const uint32_t doc = active ? (uint32_t)(rel_base + surv[(r0 + i) & ring_mask]) : 0u;
+    double tr = 0.0, br = 0.0;
+    bool first_t = true, first_b = true;
+    for (uint32_t l0 = 0; l0 < n_lists; l0 += 4) {
+      const uint32_t l = l0 + gl;
+      float w = 0.0f;
+      const bool found = active && l < n_lists && find_in_list(p, s, l, doc, slab_lo, slab_docs, w);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool fj = __shfl_sync(0xFFFFFFFFu, found ? 1 : 0, j, 4) != 0;
+        const double wj = (double)__shfl_sync(0xFFFFFFFFu, w, j, 4);
+        if (!fj) continue;
+        if ((l0 + j) & 1u) {
+          br = first_b ? wj : __dadd_rn(br, wj);
+          first_b = false;
+        } else {
+          tr = first_t ? wj : __dadd_rn(tr, wj);
+          first_t = false;
+        }
       }
-    } else {
-      hi = pos;
-      uint32_t step = 16;
-      lo = hi;
-      while (true) {
-        lo = hi > step ? hi - step : 0u;
-        if (lo == 0 || docs[lo - 1] < doc) break;
-        hi = lo - 1;
-        step <<= 1;
-      }
     }
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (docs[mid] < doc) lo = mid + 1; else hi = mid;
-    }
-    if (lo == len || docs[lo] != doc) continue;
-    const double w = (double)p.tab[l & 1].w[s.base[l] + lo];
-    if (l & 1u) {
-      br = first_b ? w : __dadd_rn(br, w);
-      first_b = false;
-    } else {
-      tr = first_t ? w : __dadd_rn(tr, w);
-      first_t = false;
-    }
+    if (active && gl == 0) finish_exact(p, s, q, doc, tr, br, qm, k);
   }
 }
 
@@ -867,12 +891,7 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
       const uint32_t surv_end = s.n_list;
       for (uint32_t r0 = surv_done; r0 != surv_end; r0 += min((uint32_t)kCand, surv_end - r0)) {
         const uint32_t n_round = min((uint32_t)kCand, surv_end - r0);
-        for (uint32_t i = tid; i < n_round; i += kT) {
-          const uint32_t doc = (uint32_t)(slab_lo + surv[(r0 + i) & ring_mask]);
-          double tr, br;
-          exact_sums(p, s, n_lists, doc, slab_lo, slab_hi - slab_lo, tr, br);
-          finish_exact(p, s, q, doc, tr, br, qm, k);
-        }
+        evaluate_survivors(p, s, q, surv, ring_mask, r0, n_round, slab_lo, n_lists, slab_lo, slab_hi - slab_lo, qm, k);
         __syncthreads();
         if (s.n_cand) merge_candidates(s, k);
       }
@@ -980,12 +999,7 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
       const uint64_t rel_base = flush_each ? d0 : slab_lo;
       for (uint32_t r0 = surv_done; r0 != surv_end; r0 += min((uint32_t)kCand, surv_end - r0)) {
         const uint32_t cnt = min((uint32_t)kCand, surv_end - r0);
-        for (uint32_t i = tid; i < cnt; i += kT) {
-          const uint32_t doc = (uint32_t)(rel_base + surv[(r0 + i) & (kRing - 1)]);
-          double tr, br;
-          exact_sums(p, s, n_lists, doc, slab_lo, slab_hi - slab_lo, tr, br);
-          finish_exact(p, s, q, doc, tr, br, qm, k);
-        }
+        evaluate_survivors(p, s, q, surv, kRing - 1, r0, cnt, rel_base, n_lists, slab_lo, slab_hi - slab_lo, qm, k);
         __syncthreads();
         if (s.n_cand) merge_candidates(s, k);
       }
