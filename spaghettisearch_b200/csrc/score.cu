@@ -2,25 +2,21 @@
 // (retrieval/main_retrieve.go:15-104, get_metadata.go:16-77, phrase.go:11-170,
 // util.go:48-54,179-203) for a whole query batch.
 //
-// One CTA scores one (query, doc slab) pair.  The slab is walked in sub-ranges
-// of kRange docs whose two fp64 accumulators (TitleRank, BodyRank) live in
-// shared memory.  Per sub-range:
-//   1. every posting list of the query is narrowed to the sub-range by a
-//      galloping search from where the previous sub-range ended;
-//   2. keyword tokens are applied in query order, body and title lists
-//      together, a barrier between tokens: a list holds a doc at most once, so
-//      no atomics are needed and each doc's sum has the reference's token order
-//      (main_retrieve.go:61-69, 170-187);
-//   3. the phrase (main_retrieve.go:73-78, phrase.go) is applied last: the
-//      shortest list drives, the others are probed by binary search, positions
-//      are intersected with the reference's shifted-equality rule;
-//   4. matched docs are finished -- cosine, NaN -> 0, PageRank blend
-//      (get_metadata.go:53-69) -- and the few that beat the CTA's running k-th
-//      best go through a rank-by-counting merge into the running top-k.
-// CTAs are ordered slab-major so that concurrently running CTAs read the same
-// slice of the index and of the per-doc norms (L2 reuse across queries).
-// A final kernel merges the per-slab lists; the same kernel merges per-shard
-// lists for the doc-sharded multi-GPU path.
+// One CTA scores one (query, group of doc slabs) pair.  Every path does the same two things: find
+// the docs whose score could reach the running k-th best with cheap, conservative fp32/fp16 bounds,
+// then evaluate those docs exactly (finish_exact: fp64 sums of the fp32 weights in query-token
+// order, cosine, NaN -> 0, PageRank blend, get_metadata.go:53-69).  Paths, by (query, range):
+//   owner_path  few postings, no phrase: lists staged in shared memory, lookups between the sorted
+//               lists, the first list holding a doc folds its weights in list order;
+//   dtiv_path   keyword query with a dense term: the term's contribution to the bound is one fp16
+//               impact per doc, streamed; sparse tokens staged or scattered; survivors looked up;
+//   accumulator path (in k_score): sub-ranges of kRange docs with two fp64 accumulators in shared
+//               memory, tokens applied in query order, phrase (phrase.go) last, matched-doc list;
+//   sort_path   sparse ranges of phrase queries (bitonic sort of tagged postings).
+// k_narrow finds every list's offsets at the slab boundaries once per batch, k_plan groups the slabs
+// per query, CTAs are ordered slab-major (co-resident CTAs read the same slice of the index), a running
+// per-query bound is shared across slabs, k_merge merges the per-slab lists; the same kernel merges
+// per-shard lists for the doc-sharded multi-GPU path.  DESIGN.md section 5 has the reasoning and numbers.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
