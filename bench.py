@@ -138,6 +138,8 @@ def run_ours(args):
     from spaghettisearch_b200 import capi, sharding, synth
 
     rank, local, world = dist_env(args)
+    # stdout carries exactly one JSON line: NCCL's own banner/debug lines go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
