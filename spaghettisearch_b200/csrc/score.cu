@@ -663,14 +663,27 @@ __device__ __forceinline__ bool dtiv_stream_slab(const ScoreParams& p, Smem& s, 
   for (int i = 0; i < (ND ? ND : 1); ++i) base[i] = p.uvec + (size_t)s.dense_slots[i] * p.d_pad + slab_lo;
   const uint16_t* __restrict__ zv = p.zvec + slab_lo;
   bool ovf = false;
-  auto process = [&](const float (&sum)[8], uint32_t off) {
-    uint32_t present = 0;
+  auto process = [&](float (&sum)[8], uint32_t off) {
+    // a doc is present iff its impact sum is > 0 (impacts are >= 0 and > 0 for a posting); docs past the
+    // slab end or owned by the sparse-token pass are made absent by clearing their sums (rare branches)
+    if (off + 8 > n_docs) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) present |= (sum[j] > 0.0f ? 1u : 0u) << j;  // impacts are >= 0, > 0 for a posting
-    if (excl) present &= ~((excl[off >> 5] >> (off & 31)) & 0xFFu);
-    if (off + 8 > n_docs) present &= (1u << (n_docs - off)) - 1u;
-    if (!present) return;
-    my_matched += __popc(present);
+      for (int j = 0; j < 8; ++j)
+        if (off + j >= n_docs) sum[j] = 0.0f;
+    }
+    if (excl) {
+      const uint32_t ex = (excl[off >> 5] >> (off & 31)) & 0xFFu;
+      if (ex) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if ((ex >> j) & 1u) sum[j] = 0.0f;
+      }
+    }
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cnt += min(__float_as_uint(sum[j]), 1u);  // sums are non-negative floats
+    if (!cnt) return;
+    my_matched += cnt;
     const float gmax = fmaxf(fmaxf(fmaxf(sum[0], sum[1]), fmaxf(sum[2], sum[3])),
                              fmaxf(fmaxf(sum[4], sum[5]), fmaxf(sum[6], sum[7])));
     {
@@ -681,7 +694,7 @@ __device__ __forceinline__ bool dtiv_stream_slab(const ScoreParams& p, Smem& s, 
     const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (!((present >> j) & 1u)) continue;
+      if (!(sum[j] > 0.0f)) continue;
       const float z = half_bits_to_float(j & 1 ? zw[j >> 1] >> 16 : zw[j >> 1] & 0xFFFFu);
       const float a = blend_scale * z, b = qf_inv * sum[j];
       if ((a + b) + (fabsf(a) + fabsf(b)) * 1e-4f + 1e-30f < thr_f) continue;  // NaN and +inf stay in
