@@ -58,6 +58,7 @@ struct ScoreParams {
   const uint32_t* narrow;  // [list][n_slabs+1] posting offset (from the term's row start) of every slab boundary
   uint32_t sort_max;     // slabs with at most this many postings take the sort path (<= kSortMax)
   int owner_path;        // phrase-free sparse slabs: lookups in the sorted lists instead of a sort
+  int phrase_dense;      // phrase queries may take the impact-vector path (SS_SCORE_PHRASE_DENSE)
   const double* sqd;     // [D] blend term for a shared topic vector, or NULL
   const double* pr;      // [D][T] for per-query topic vectors
   const double* probs;   // [n_q][T] when per-query
@@ -134,10 +135,10 @@ struct Smem {
   float thr_f;  // fp32 lower bound of the score a doc needs: max(local k-th best, the query's running bound)
   unsigned long long gkey;  // the query's running bound (score key of some slab's k-th best), 0 = none
   float gthr_f;             // its score rounded down to fp32 (-inf when none)
-  uint8_t tok_dense[kMaxKw];   // dense slot of every keyword token (255 = sparse)
-  uint8_t dense_slots[kMaxKw]; // the dense tokens' slots, in token order
-  uint8_t sparse_toks[kMaxKw]; // indices of the sparse tokens
-  uint32_t n_dense_tok, n_sparse_tok;
+  uint8_t tok_dense[kMaxKw + kMaxPh];   // dense slot of every token, keyword then phrase (255 = sparse)
+  uint8_t dense_slots[kMaxKw + kMaxPh]; // the dense tokens' slots, in token order
+  uint8_t sparse_toks[kMaxKw + kMaxPh]; // indices of the sparse tokens
+  uint32_t n_dense_tok, n_sparse_tok, n_dense_kw;
   float zred[kT / 32];
 };
 
@@ -572,8 +573,8 @@ __device__ __forceinline__ float half_bits_to_float(uint32_t h) {
 
 // The doc's weight in list l of the query (slab range), if it has one: interpolation start (docs are
 // spread over the slab), gallop to bracket the doc, bisect.
-__device__ __forceinline__ bool find_in_list(const ScoreParams& p, const Smem& s, uint32_t l, uint32_t doc,
-                                             uint64_t slab_lo, uint64_t slab_docs, float& w_out) {
+__device__ __forceinline__ bool find_index_in_list(const ScoreParams& p, const Smem& s, uint32_t l, uint32_t doc,
+                                                   uint64_t slab_lo, uint64_t slab_docs, unsigned long long& at) {
   const uint32_t len = s.len[l];
   if (!len) return false;
   const uint32_t* __restrict__ docs = p.tab[l & 1].doc_ids + s.base[l];
@@ -603,7 +604,46 @@ __device__ __forceinline__ bool find_in_list(const ScoreParams& p, const Smem& s
     if (docs[mid] < doc) lo = mid + 1; else hi = mid;
   }
   if (lo == len || docs[lo] != doc) return false;
-  w_out = p.tab[l & 1].w[s.base[l] + lo];
+  at = s.base[l] + lo;
+  return true;
+}
+__device__ __forceinline__ bool find_in_list(const ScoreParams& p, const Smem& s, uint32_t l, uint32_t doc,
+                                             uint64_t slab_lo, uint64_t slab_docs, float& w_out) {
+  unsigned long long at;
+  if (!find_index_in_list(p, s, l, doc, slab_lo, slab_docs, at)) return false;
+  w_out = p.tab[l & 1].w[at];
+  return true;
+}
+
+// phrase.go:53-109 for ONE doc and one table (the per-doc form of apply_phrase): lists l0+2*i+tb hold
+// token i.  The doc gets one weight = fp32 sum of the tokens' weights in phrase order iff every token has
+// a posting of the doc in this table and some position a of token 0 has a + i among token i's positions
+// (compared as (pos_i - float32(i)) == pos_0, phrase.go:144-146, util.go:185).
+__device__ bool phrase_hit(const ScoreParams& p, const Smem& s, int tb, uint32_t l0, uint32_t L, uint32_t doc,
+                           uint64_t slab_lo, uint64_t slab_docs, float& sum_out) {
+  const TableView& tv = p.tab[tb];
+  if (!tv.pos_ptr) return false;
+  unsigned long long pi[kMaxPh];
+  for (uint32_t i = 0; i < L; ++i)
+    if (!find_index_in_list(p, s, l0 + 2 * i + tb, doc, slab_lo, slab_docs, pi[i])) return false;
+  bool hit = false;
+  const unsigned long long a0 = tv.pos_ptr[pi[0]], a1 = tv.pos_ptr[pi[0] + 1];
+  for (unsigned long long x = a0; x < a1 && !hit; ++x) {
+    const float a = __fadd_rn(tv.pos[x], -0.0f);
+    bool ok = true;
+    for (uint32_t i = 1; i < L && ok; ++i) {
+      const float shift = (float)(uint8_t)i;
+      bool found = false;
+      for (unsigned long long y = tv.pos_ptr[pi[i]]; y < tv.pos_ptr[pi[i] + 1] && !found; ++y)
+        found = __fadd_rn(tv.pos[y], -shift) == a;
+      ok = found;
+    }
+    hit = ok;
+  }
+  if (!hit) return false;
+  float sum = 0.0f;  // phrase.go:59,69,83: float32 running sum in token order
+  for (uint32_t i = 0; i < L; ++i) sum = __fadd_rn(sum, tv.w[pi[i]]);
+  sum_out = sum;
   return true;
 }
 
@@ -612,8 +652,9 @@ __device__ __forceinline__ bool find_in_list(const ScoreParams& p, const Smem& s
 // as the accumulator paths -- and the group's first lane finishes the doc.  Every thread of the CTA calls.
 __device__ __forceinline__ void evaluate_survivors(const ScoreParams& p, Smem& s, uint32_t q, const uint16_t* surv,
                                                    uint32_t ring_mask, uint32_t r0, uint32_t n, uint64_t rel_base,
-                                                   uint32_t n_lists, uint64_t slab_lo, uint64_t slab_docs, double qm,
-                                                   uint32_t k) {
+                                                   uint32_t n_kw, uint32_t n_ph, uint64_t slab_lo, uint64_t slab_docs,
+                                                   double qm, uint32_t k) {
+  const uint32_t n_lists = 2 * n_kw;  // keyword lists; the phrase is evaluated after them
   const uint32_t sub = threadIdx.x >> 2, gl = threadIdx.x & 3;
   for (uint32_t base = 0; base < n; base += kT / 4) {
     const uint32_t i = base + sub;
@@ -639,7 +680,21 @@ __device__ __forceinline__ void evaluate_survivors(const ScoreParams& p, Smem& s
         }
       }
     }
-    if (active && gl == 0) finish_exact(p, s, q, doc, tr, br, qm, k);
+    if (active && gl == 0) {
+      bool matched = !(first_t && first_b);  // a keyword posting
+      if (n_ph) {  // the phrase's weight is appended after the keyword weights (main_retrieve.go:73-78)
+        float ws = 0.0f;
+        if (phrase_hit(p, s, 1, 2 * n_kw, n_ph, doc, slab_lo, slab_docs, ws)) {
+          br = first_b ? (double)ws : __dadd_rn(br, (double)ws);
+          matched = true;
+        }
+        if (phrase_hit(p, s, 0, 2 * n_kw, n_ph, doc, slab_lo, slab_docs, ws)) {
+          tr = first_t ? (double)ws : __dadd_rn(tr, (double)ws);
+          matched = true;
+        }
+      }
+      if (matched) finish_exact(p, s, q, doc, tr, br, qm, k);
+    }
   }
 }
 
@@ -746,14 +801,17 @@ __device__ __forceinline__ bool dtiv_stream_slab(const ScoreParams& p, Smem& s, 
 }
 
 __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t slab_lo, uint64_t slab_hi, uint32_t n_kw,
-                          double qm, float qf_inv, float blend_scale, uint32_t k, unsigned long long& n_postings,
-                          unsigned long long& n_matched) {
+                          uint32_t n_ph, double qm, float qf_inv, float blend_scale, uint32_t k,
+                          unsigned long long& n_postings, unsigned long long& n_matched) {
+  // Phrase tokens take part in the bound like keyword tokens: the phrase adds at most the sum of its
+  // tokens' weights per table (phrase.go:97-106), and only if the positions line up, which the exact
+  // evaluation of the survivors decides.  "Present" then means "has a posting of some query token".
   constexpr int RD = kDenseRange;
   constexpr uint32_t kRing = 2 * RD;                               // survivor ring capacity
   float* sacc = reinterpret_cast<float*>(&s.acc[0][0]);            // [RD] sparse tokens' impact sums
   uint16_t* surv = reinterpret_cast<uint16_t*>(&s.acc[1][0]);      // [kRing] slab-relative slots >> 0 of survivors
   uint32_t* dbits = s.dbits;                                       // [RD / 32] presence from sparse tokens
-  const uint32_t tid = threadIdx.x, n_lists = 2 * n_kw;
+  const uint32_t tid = threadIdx.x, n_lists = 2 * (n_kw + n_ph);
   const uint32_t nd = s.n_dense_tok, nsp = s.n_sparse_tok;
   const uint32_t n_sub = (uint32_t)((slab_hi - slab_lo + RD - 1) / RD);
   if (tid == 0) {
@@ -900,7 +958,7 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
       const uint32_t surv_end = s.n_list;
       for (uint32_t r0 = surv_done; r0 != surv_end; r0 += min((uint32_t)kCand, surv_end - r0)) {
         const uint32_t n_round = min((uint32_t)kCand, surv_end - r0);
-        evaluate_survivors(p, s, q, surv, ring_mask, r0, n_round, slab_lo, n_lists, slab_lo, slab_hi - slab_lo, qm, k);
+        evaluate_survivors(p, s, q, surv, ring_mask, r0, n_round, slab_lo, n_kw, n_ph, slab_lo, slab_hi - slab_lo, qm, k);
         __syncthreads();
         if (s.n_cand) merge_candidates(s, k);
       }
@@ -1008,7 +1066,7 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
       const uint64_t rel_base = flush_each ? d0 : slab_lo;
       for (uint32_t r0 = surv_done; r0 != surv_end; r0 += min((uint32_t)kCand, surv_end - r0)) {
         const uint32_t cnt = min((uint32_t)kCand, surv_end - r0);
-        evaluate_survivors(p, s, q, surv, kRing - 1, r0, cnt, rel_base, n_lists, slab_lo, slab_hi - slab_lo, qm, k);
+        evaluate_survivors(p, s, q, surv, kRing - 1, r0, cnt, rel_base, n_kw, n_ph, slab_lo, slab_hi - slab_lo, qm, k);
         __syncthreads();
         if (s.n_cand) merge_candidates(s, k);
       }
@@ -1058,13 +1116,15 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
   }
   // which keyword tokens have an impact vector
   if (tid == 0) {
-    uint32_t ndt = 0, nst = 0;
-    for (uint32_t i = 0; i < n_kw; ++i) {
-      const uint32_t term = p.kw_terms[kb + i];
+    uint32_t ndt = 0, nst = 0, ndk = 0;
+    for (uint32_t i = 0; i < n_tok; ++i) {
+      const uint32_t term = i < n_kw ? p.kw_terms[kb + i] : p.ph_terms[pb + (i - n_kw)];
       const uint8_t slot = (p.uvec && term < p.dense_map_V) ? p.dense_map[term] : (uint8_t)255;
       s.tok_dense[i] = slot;
       if (slot != 255) s.dense_slots[ndt++] = slot; else s.sparse_toks[nst++] = (uint8_t)i;
+      if (slot != 255 && i < n_kw) ++ndk;
     }
+    s.n_dense_kw = ndk;
     s.n_dense_tok = ndt;
     s.n_sparse_tok = nst;
   }
@@ -1105,9 +1165,12 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
 
   if (work == 0) {
     // nothing of this query lives in this slab
-  } else if (n_ph == 0 && s.n_dense_tok > 0 && work > p.sort_max &&
+  } else if (work > p.sort_max &&
+             // a phrase query needs a dense KEYWORD token: its many matches set the threshold the phrase
+             // docs are screened against (phrase hits alone are too rare to ever establish one)
+             (n_ph ? (p.phrase_dense && s.n_dense_kw > 0) : s.n_dense_tok > 0) &&
              2 * s.n_sparse_tok * ((slab_hi - slab_lo + kDenseRange - 1) / kDenseRange + 1) <= (uint64_t)kBounds) {
-    dtiv_path(p, s, q, slab_lo, slab_hi, n_kw, qm, qf_inv, blend_scale, k, n_postings, n_matched);
+    dtiv_path(p, s, q, slab_lo, slab_hi, n_kw, n_ph, qm, qf_inv, blend_scale, k, n_postings, n_matched);
   } else if (work <= p.sort_max && n_ph == 0 && p.owner_path) {
     owner_path(p, s, q, slab_lo, n_kw, qm, qf_inv, blend_scale, k, n_postings, n_matched);
   } else if (work <= p.sort_max && slab_hi - slab_lo <= (1ull << 24)) {
@@ -1336,11 +1399,13 @@ __global__ void k_plan(ScoreParams p, uint32_t merge_max, uint8_t* __restrict__ 
   };
   // keyword queries with a dense term: the impact-vector path streams up to 65536 docs per CTA
   bool dense_q = false;
-  if (p.uvec && !(p.ph_ptr && p.ph_ptr[q + 1] > pb))
+  if (p.uvec) {
     for (uint64_t i = kb; i < p.kw_ptr[q + 1] && !dense_q; ++i) {
       const uint32_t term = p.kw_terms[i];
       dense_q = term < p.dense_map_V && p.dense_map[term] != 255;
     }
+    if (p.ph_ptr && p.ph_ptr[q + 1] > pb && !p.phrase_dense) dense_q = false;
+  }
   const uint32_t dense_len = dense_q ? (uint32_t)max((uint64_t)1, min((uint64_t)255, 65536 / p.slab_docs)) : 1u;
   uint8_t* out = group_len + (size_t)q * p.n_slabs;
   uint32_t sl = 0;
@@ -1754,6 +1819,8 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   ScoreParams p{};
   p.sort_max = kSortMax;
   p.owner_path = 1;
+  p.phrase_dense = 1;
+  if (const char* env = getenv("SS_SCORE_PHRASE_DENSE")) p.phrase_dense = atoi(env);
   if (const char* env = getenv("SS_SCORE_OWNER")) p.owner_path = atoi(env);
   if (const char* env = getenv("SS_SCORE_SORT_MAX")) p.sort_max = std::min<uint32_t>(kSortMax, (uint32_t)atoi(env));
   p.meta32 = ix->meta32.p;

@@ -159,6 +159,7 @@ def test_hot_terms_many_ties(engine, synth_index):
     {"SS_SCORE_SORT_MAX": "0", "SS_SCORE_DENSE_MAX": "3"},   # 3 dense terms: mixed dense + scattered sparse tokens
     {"SS_SCORE_SORT_MAX": "0", "SS_SCORE_DENSE_FRAC": "100000"},  # every term with a posting is "dense" (up to 224)
     {"SS_SCORE_QTHR": "0", "SS_SCORE_OWNER": "0"},        # first-version sparse path, no cross-slab bound
+    {"SS_SCORE_PHRASE_DENSE": "0"},                       # phrase queries on the accumulator / sort paths only
 ])
 def test_scoring_paths_agree_with_oracle(engine, synth_index, monkeypatch, env):
     # The execution paths of ss_score_batch differ only in HOW they find the docs worth an exact
@@ -176,6 +177,15 @@ def test_scoring_paths_agree_with_oracle(engine, synth_index, monkeypatch, env):
                 got = engine.score_batch(kw_ptr, kw, topic_probs=tp, k=k)
                 ref = O.score_batch(s["ot"], s["ob"], s["D"], s["tmag"], s["bmag"], pr, kw_ptr, kw, topic_probs=tp, k=k)
                 assert_same_results(got, ref)
+    # phrase queries: with a dense keyword token they take the impact-vector path too (the phrase tokens
+    # enter the bound, the positions are checked for the survivors); hot terms 0..3 make that common
+    qp = synth.queries(600, s["V"], phrase_fraction=0.5, seed=49)
+    hp = queries_csr([[0], [1, 0], [0, 2], [5000, 1], [0], [2, 2]], [[1, 2], [2, 3], [0, 1, 2], [0, 1], [7, 300], [2]])
+    engine.set_pagerank(None)
+    for kw_ptr, kw, ph_ptr, ph in ((qp.kw_ptr, qp.kw_terms, qp.ph_ptr, qp.ph_terms), hp):
+        got = engine.score_batch(kw_ptr, kw, ph_ptr, ph, k=10)
+        ref = O.score_batch(s["ot"], s["ob"], s["D"], s["tmag"], s["bmag"], None, kw_ptr, kw, ph_ptr, ph, k=10)
+        assert_same_results(got, ref)
     for key in env:
         monkeypatch.delenv(key)
     engine.set_pagerank(None)
