@@ -238,7 +238,7 @@ __device__ __forceinline__ void mark_matched(Smem& s, uint32_t slot) {
 // of token 0 has a + i among token i's positions (compared as
 // (pos_i - float32(i)) == pos_0, phrase.go:144-146, util.go:185).
 // EMIT = false: add into the sub-range accumulators; EMIT = true: append a sort entry.
-template <bool EMIT>
+template <int EMIT>
 __device__ void apply_phrase(const ScoreParams& p, Smem& s, int tb, uint32_t l0, uint32_t L, uint64_t d0,
                              uint32_t seq, unsigned long long& n_postings) {
   const TableView& tv = p.tab[tb];
@@ -293,9 +293,13 @@ __device__ void apply_phrase(const ScoreParams& p, Smem& s, int tb, uint32_t l0,
     float sum = 0.0f;  // phrase.go:59,69,83: float32 running sum in token order
     for (uint32_t i = 0; i < L; ++i) sum = __fadd_rn(sum, tv.w[pi[i]]);
     const uint32_t slot = (uint32_t)(doc - d0);
-    if (EMIT) {
+    if (EMIT == 1) {
       unsigned long long* ent = reinterpret_cast<unsigned long long*>(&s.acc[0][0]);
       ent[atomicAdd(&s.n_ent, 1u)] = make_entry(slot, seq, sum);
+    } else if (EMIT == 2) {  // lookup path: (doc offset, weight) appended from position `seq` of its arrays
+      const uint32_t at = seq + atomicAdd(&s.n_ent, 1u);
+      reinterpret_cast<uint32_t*>(&s.acc[0][0])[at] = slot;
+      reinterpret_cast<float*>(&s.acc[1][0])[at] = sum;
     } else {
       s.acc[tb][slot] = __dadd_rn(s.acc[tb][slot], (double)sum);
       mark_matched(s, slot);
@@ -432,8 +436,8 @@ __device__ void sort_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
   }
   if (tid == 0) n_postings += total_kw;
   if (n_ph) {
-    apply_phrase<true>(p, s, 1, n_kw_lists, n_ph, slab_lo, n_kw_lists + 1, n_postings);
-    apply_phrase<true>(p, s, 0, n_kw_lists, n_ph, slab_lo, n_kw_lists, n_postings);
+    apply_phrase<1>(p, s, 1, n_kw_lists, n_ph, slab_lo, n_kw_lists + 1, n_postings);
+    apply_phrase<1>(p, s, 0, n_kw_lists, n_ph, slab_lo, n_kw_lists, n_postings);
   }
   __syncthreads();
   const uint32_t n = s.n_ent;
@@ -484,24 +488,34 @@ __device__ void sort_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
 // sums, and finishes the doc.  No sort, no barriers inside the loop: the bitonic sort this
 // replaces cost ~100 ps per posting against ~10 ps in the dense path (78 block barriers per
 // 4096 entries), and 44 % of the benchmark's query tokens take this path.
-__device__ void owner_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t slab_lo, uint32_t n_kw, double qm,
-                           float qf_inv, float blend_scale, uint32_t k, unsigned long long& n_postings,
+__device__ void owner_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t slab_lo, uint32_t n_kw, uint32_t n_ph,
+                           double qm, float qf_inv, float blend_scale, uint32_t k, unsigned long long& n_postings,
                            unsigned long long& n_matched) {
   uint32_t* soff = reinterpret_cast<uint32_t*>(&s.acc[0][0]);  // [kSortMax] doc offset in the slab
   float* sw = reinterpret_cast<float*>(&s.acc[1][0]);          // [kSortMax] weight
-  const uint32_t tid = threadIdx.x, n_lists = 2 * n_kw;
+  const uint32_t tid = threadIdx.x, n_kw_lists = 2 * n_kw;
+  // With a phrase, its hits form two more "lists" behind the keyword lists: title hits (even index, so
+  // their weight joins TitleRank) then body hits (odd), each weight appended after the keyword weights as
+  // in main_retrieve.go:73-78.  They fit: a table's hits are at most its shortest phrase list, which is
+  // what `work` counted.
+  const uint32_t n_lists = n_kw_lists + (n_ph ? 2u : 0u);
   if (tid == 0) {
     uint32_t run = 0;
-    for (uint32_t l = 0; l < n_lists; ++l) {
+    for (uint32_t l = 0; l < n_kw_lists; ++l) {
       s.bounds[l] = run;
       run += s.len[l];
     }
-    s.bounds[n_lists] = run;
+    s.bounds[n_kw_lists] = run;
+    s.n_ent = 0;
+  }
+  for (uint32_t l = n_kw_lists + tid; l < n_kw_lists + 2 * n_ph; l += kT) {  // phrase lists: whole range
+    s.cur[l] = s.base[l];
+    s.hi[l] = s.base[l] + s.len[l];
   }
   __syncthreads();
-  const uint32_t total = s.bounds[n_lists];
+  const uint32_t kw_total = s.bounds[n_kw_lists];
   // stage: list by list, coalesced
-  for (uint32_t l = 0; l < n_lists; ++l) {
+  for (uint32_t l = 0; l < n_kw_lists; ++l) {
     const uint32_t len = s.len[l];
     if (!len) continue;
     const TableView& tv = p.tab[l & 1];
@@ -512,8 +526,41 @@ __device__ void owner_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t s
       sw[o + i] = tv.w[at + i];
     }
   }
-  if (tid == 0) n_postings += total;
-  __syncthreads();
+  if (tid == 0) n_postings += kw_total;
+  if (n_ph) {
+    // phrase hits of the title table, then of the body table, each sorted by doc (ranking by counting:
+    // a table holds a doc once, so the ranks are a permutation)
+    for (int tb = 0; tb < 2; ++tb) {
+      const uint32_t start = tb == 0 ? kw_total : s.bounds[n_kw_lists + 1];
+      apply_phrase<2>(p, s, tb, n_kw_lists, n_ph, slab_lo, start, n_postings);
+      __syncthreads();
+      const uint32_t cnt = s.n_ent;
+      uint32_t my_off[kSortMax / kT], my_rank[kSortMax / kT];
+      float my_w[kSortMax / kT];
+#pragma unroll 1
+      for (uint32_t c = 0, i = tid; i < cnt; i += kT, ++c) {
+        my_off[c] = soff[start + i];
+        my_w[c] = sw[start + i];
+        uint32_t r = 0;
+        for (uint32_t j = 0; j < cnt; ++j) r += soff[start + j] < my_off[c] ? 1u : 0u;
+        my_rank[c] = r;
+      }
+      __syncthreads();
+#pragma unroll 1
+      for (uint32_t c = 0, i = tid; i < cnt; i += kT, ++c) {
+        soff[start + my_rank[c]] = my_off[c];
+        sw[start + my_rank[c]] = my_w[c];
+      }
+      if (tid == 0) {
+        s.bounds[n_kw_lists + tb + 1] = start + cnt;
+        s.n_ent = 0;
+      }
+      __syncthreads();
+    }
+  } else {
+    __syncthreads();
+  }
+  const uint32_t total = s.bounds[n_lists];
   // position of doc offset `off` in list j, or kNoDoc
   auto find = [&](uint32_t j, uint32_t off) -> uint32_t {
     uint32_t lo = s.bounds[j], hi = s.bounds[j + 1];
@@ -1171,8 +1218,8 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
              (n_ph ? (p.phrase_dense && s.n_dense_kw > 0) : s.n_dense_tok > 0) &&
              2 * s.n_sparse_tok * ((slab_hi - slab_lo + kDenseRange - 1) / kDenseRange + 1) <= (uint64_t)kBounds) {
     dtiv_path(p, s, q, slab_lo, slab_hi, n_kw, n_ph, qm, qf_inv, blend_scale, k, n_postings, n_matched);
-  } else if (work <= p.sort_max && n_ph == 0 && p.owner_path) {
-    owner_path(p, s, q, slab_lo, n_kw, qm, qf_inv, blend_scale, k, n_postings, n_matched);
+  } else if (work <= p.sort_max && p.owner_path && (n_ph == 0 || slab_hi - slab_lo <= 0xFFFFFFFFull)) {
+    owner_path(p, s, q, slab_lo, n_kw, n_ph, qm, qf_inv, blend_scale, k, n_postings, n_matched);
   } else if (work <= p.sort_max && slab_hi - slab_lo <= (1ull << 24)) {
     sort_path(p, s, q, slab_lo, n_kw, n_ph, qm, qf_inv, blend_scale, k, n_postings, n_matched);
   } else {
@@ -1232,8 +1279,8 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
         }
         __syncthreads();
         any = true;
-        apply_phrase<false>(p, s, 1, 2 * n_kw, n_ph, d0, 0, n_postings);
-        apply_phrase<false>(p, s, 0, 2 * n_kw, n_ph, d0, 0, n_postings);
+        apply_phrase<0>(p, s, 1, 2 * n_kw, n_ph, d0, 0, n_postings);
+        apply_phrase<0>(p, s, 0, 2 * n_kw, n_ph, d0, 0, n_postings);
       }
     }
     if (!any) continue;  // uniform
