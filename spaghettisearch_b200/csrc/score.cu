@@ -765,27 +765,14 @@ __device__ __forceinline__ bool dtiv_stream_slab(const ScoreParams& p, Smem& s, 
   for (int i = 0; i < (ND ? ND : 1); ++i) base[i] = p.uvec + (size_t)s.dense_slots[i] * p.d_pad + slab_lo;
   const uint16_t* __restrict__ zv = p.zvec + slab_lo;
   bool ovf = false;
-  auto process = [&](float (&sum)[8], uint32_t off) {
-    // a doc is present iff its impact sum is > 0 (impacts are >= 0 and > 0 for a posting); docs past the
-    // slab end or owned by the sparse-token pass are made absent by clearing their sums (rare branches)
-    if (off + 8 > n_docs) {
+  auto process = [&](const float (&sum)[8], uint32_t off) {
+    uint32_t present = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (off + j >= n_docs) sum[j] = 0.0f;
-    }
-    if (excl) {
-      const uint32_t ex = (excl[off >> 5] >> (off & 31)) & 0xFFu;
-      if (ex) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if ((ex >> j) & 1u) sum[j] = 0.0f;
-      }
-    }
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) cnt += min(__float_as_uint(sum[j]), 1u);  // sums are non-negative floats
-    if (!cnt) return;
-    my_matched += cnt;
+    for (int j = 0; j < 8; ++j) present |= (sum[j] > 0.0f ? 1u : 0u) << j;  // impacts are >= 0, > 0 for a posting
+    if (excl) present &= ~((excl[off >> 5] >> (off & 31)) & 0xFFu);
+    if (off + 8 > n_docs) present &= (1u << (n_docs - off)) - 1u;
+    if (!present) return;
+    my_matched += __popc(present);
     const float gmax = fmaxf(fmaxf(fmaxf(sum[0], sum[1]), fmaxf(sum[2], sum[3])),
                              fmaxf(fmaxf(sum[4], sum[5]), fmaxf(sum[6], sum[7])));
     {
@@ -796,7 +783,7 @@ __device__ __forceinline__ bool dtiv_stream_slab(const ScoreParams& p, Smem& s, 
     const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (!(sum[j] > 0.0f)) continue;
+      if (!((present >> j) & 1u)) continue;
       const float z = half_bits_to_float(j & 1 ? zw[j >> 1] >> 16 : zw[j >> 1] & 0xFFFFu);
       const float a = blend_scale * z, b = qf_inv * sum[j];
       if ((a + b) + (fabsf(a) + fabsf(b)) * 1e-4f + 1e-30f < thr_f) continue;  // NaN and +inf stay in
@@ -1124,6 +1111,9 @@ __device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t sl
   n_matched += my_matched;
 }
 
+// PHRASE = false: the batch has no phrase token; that instantiation carries none of the phrase code (the
+// keyword paths lose ~9 % to register pressure and code size otherwise).
+template <bool PHRASE>
 __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
@@ -1132,9 +1122,9 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
   if (glen == 0) return;  // scored by the CTA that leads this slab's group (its part_count stays 0)
   const uint32_t tid = threadIdx.x;
   const uint64_t kb = p.kw_ptr[q], ke = p.kw_ptr[q + 1];
-  const uint64_t pb = p.ph_ptr ? p.ph_ptr[q] : 0, pe = p.ph_ptr ? p.ph_ptr[q + 1] : 0;
+  const uint64_t pb = (PHRASE && p.ph_ptr) ? p.ph_ptr[q] : 0, pe = (PHRASE && p.ph_ptr) ? p.ph_ptr[q + 1] : 0;
   const uint32_t n_kw = (uint32_t)(ke - kb);
-  uint32_t n_ph = (uint32_t)(pe - pb);
+  uint32_t n_ph = PHRASE ? (uint32_t)(pe - pb) : 0u;
   const uint32_t q_len = n_kw + n_ph;            // main_retrieve.go:90
   if (n_ph > kMaxPh) n_ph = 0;                   // host rejects 33..256; >256 can never match (uint8 TermPos)
   const uint32_t n_tok = n_kw + n_ph, n_lists = 2 * n_tok;
@@ -1816,7 +1806,8 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   if (timing)
     for (auto& x : ws.ev)
       if (!x) SS_CUDA(cudaEventCreate(&x));
-  SS_CUDA(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  SS_CUDA(cudaFuncSetAttribute(k_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  SS_CUDA(cudaFuncSetAttribute(k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
   SS_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeMax * 16));
 
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[0], st));
@@ -1921,7 +1912,8 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
     ++launches;
   }
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[1], st));
-  k_score<<<(unsigned)(n_q * n_slabs), kT, sizeof(Smem), st>>>(p);
+  if (n_ph) k_score<true><<<(unsigned)(n_q * n_slabs), kT, sizeof(Smem), st>>>(p);
+  else k_score<false><<<(unsigned)(n_q * n_slabs), kT, sizeof(Smem), st>>>(p);
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[2], st));
   k_merge<<<(unsigned)n_q, kT, (size_t)n_slabs * k * 16, st>>>((uint32_t)n_slabs, k, (uint32_t)n_q, 0, ws.part_doc.p,
                                                               ws.part_final.p, ws.part_pr.p, ws.part_count.p,
