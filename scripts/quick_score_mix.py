@@ -13,7 +13,7 @@ def run(name, qs):
     kw_ptr = np.zeros(len(qs) + 1, np.uint64); kw_ptr[1:] = np.cumsum([len(x) for x in qs]); kw = np.array([t for x in qs for t in x], np.uint32)
     for _ in range(2):
         e.score_batch(kw_ptr, kw, topic_probs=probs, k=10); s = e.score_stats()
-    print(f"{name:28s} Q={len(qs)} score {s.score_kernel_ms:8.2f} ms  {s.score_kernel_ms*1e3/len(qs):8.1f} us/query  postings/q {s.postings_scanned/len(qs):.0f}", flush=True)
+    print(f"{name:28s} Q={len(qs)} score {s.score_kernel_ms:8.2f} ms  {s.score_kernel_ms*1e3/len(qs):8.1f} us/query  postings/q {s.postings_scanned/len(qs):.0f} matched/q {s.docs_matched/len(qs):.0f}", flush=True)
 Q = 500
 run("hot single [r<14]", [[int(rng.integers(0, 14))] for _ in range(Q)])
 run("hot + rare", [[int(rng.integers(0, 14)), int(rng.integers(1000, V))] for _ in range(Q)])
