@@ -169,8 +169,10 @@ SS_API int ss_merge_topk(ss_engine* e, uint32_t n_lists, uint64_t n_q, uint32_t 
                          double* out_pr, uint32_t* out_count);
 
 typedef struct ss_score_stats {
-  uint64_t postings_scanned;   /* sum over queries of postings read */
-  uint64_t docs_matched;       /* sum over queries of matched docs */
+  uint64_t postings_scanned;   /* sum over queries of the postings of their lists (nominal: the impact-vector
+                                  path covers a dense term's list with 2 bytes per doc instead of reading it) */
+  uint64_t docs_matched;       /* sum over queries of matched docs (phrase queries on the impact-vector path:
+                                  docs holding a posting of any query token, an upper bound) */
   uint64_t algorithmic_bytes;  /* SURVEY.md §8(d) B_q summed over the batch */
   uint32_t launches;           /* kernels launched by the last ss_score_batch */
   double kernel_ms;            /* device time of the last batch (SS_FLAG_TIMING) */
