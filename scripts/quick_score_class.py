@@ -5,6 +5,7 @@ sys.path.insert(0, ".")
 from spaghettisearch_b200 import capi, synth
 cls = sys.argv[1] if len(sys.argv) > 1 else "hot"
 Q = int(sys.argv[2]) if len(sys.argv) > 2 else 300
+K = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 D, V = 10_000_000, 1_000_000
 title = synth.index_table(V, D, 0); body = synth.index_table(V, D, 1)
 e = capi.Engine(timing=True)
@@ -24,5 +25,5 @@ if qs is not None:
 else:
     kw_ptr, kw = q.kw_ptr, q.kw_terms
 for _ in range(3):
-    e.score_batch(kw_ptr, kw, topic_probs=probs, k=10); s = e.score_stats()
+    e.score_batch(kw_ptr, kw, topic_probs=probs, k=K); s = e.score_stats()
 print(f"{cls} Q={Q} score {s.score_kernel_ms:.2f} ms {s.score_kernel_ms*1e3/Q:.1f} us/query postings/q {s.postings_scanned/Q:.0f} ps/posting {s.score_kernel_ms*1e9/max(1,s.postings_scanned):.1f}", flush=True)

@@ -1365,57 +1365,104 @@ __global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
 
 // Merge n_lists lists of up to k results per query into one, same total order.
 // in_*: [n_q][n_lists][k] (list_major == 0) or [n_lists][n_q][k] (list_major == 1).
-constexpr int kMergeMax = 4096;
+// Every input list is sorted best first (k_score writes its running top k in rank order, and so does this
+// kernel), so this is a k-way merge: k rounds, each picks the best list head with a block-wide argmax over
+// the total order (score key descending, doc id ascending).  Cost k * (n_lists / 256 + log 256), whatever
+// the lists hold -- the first version ranked all n_lists * k entries against each other, which at k = 50
+// (half-full lists: the running bound is only a slab-local k-th best) took twice as long as the scoring.
+constexpr int kMergeMax = 16384;  // n_lists * k accepted (two bytes of shared memory per list)
 __global__ void __launch_bounds__(kT) k_merge(uint32_t n_lists, uint32_t k, uint32_t n_q, int list_major,
                                               const uint32_t* __restrict__ in_doc, const double* __restrict__ in_final,
                                               const double* __restrict__ in_pr, const uint32_t* __restrict__ in_count,
                                               uint32_t* __restrict__ out_doc, double* __restrict__ out_final,
                                               double* __restrict__ out_pr, uint32_t* __restrict__ out_count) {
-  // The valid entries are compacted first: with the per-query running bound most per-slab lists are
-  // empty or short, and ranking by counting is quadratic in the number of entries it is given.
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_raw);
-  uint32_t* doc = reinterpret_cast<uint32_t*>(key + (size_t)n_lists * k);
-  uint32_t* from = doc + (size_t)n_lists * k;
-  __shared__ uint32_t total;
-  const uint32_t q = blockIdx.x, n = n_lists * k;
-  if (threadIdx.x == 0) total = 0;
-  for (uint32_t j = threadIdx.x; j < k; j += kT) {
+  uint8_t* head = smem_raw;            // [n_lists] next unread entry of every list
+  uint8_t* cnt = smem_raw + n_lists;   // [n_lists] entries of every list (<= k <= 128)
+  __shared__ unsigned long long w_key[kT / 32];
+  __shared__ uint32_t w_doc[kT / 32], w_list[kT / 32], win_list;
+  const uint32_t q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto src_of = [&](uint32_t l, uint32_t j) -> size_t {
+    return list_major ? ((size_t)l * n_q + q) * k + j : ((size_t)q * n_lists + l) * k + j;
+  };
+  for (uint32_t l = tid; l < n_lists; l += kT) {
+    head[l] = 0;
+    cnt[l] = (uint8_t)min(k, in_count[list_major ? (size_t)l * n_q + q : (size_t)q * n_lists + l]);
+  }
+  __syncthreads();
+  // the head of the thread's first list is cached in registers (n_lists <= 256 is the common shape)
+  unsigned long long c_key = 0;
+  uint32_t c_doc = kNoDoc;
+  bool c_valid = false;
+  auto load_head = [&](uint32_t l, unsigned long long& key, uint32_t& doc) -> bool {
+    if (head[l] >= cnt[l]) return false;
+    const size_t src = src_of(l, head[l]);
+    doc = in_doc[src];
+    if (doc == kNoDoc) return false;  // padding: the list ends here
+    key = score_key(in_final[src]);
+    return true;
+  };
+  if (tid < n_lists) c_valid = load_head(tid, c_key, c_doc);
+  uint32_t n_out = 0;
+  for (uint32_t step = 0; step < k; ++step) {
+    unsigned long long b_key = c_key;
+    uint32_t b_doc = c_doc, b_list = c_valid ? tid : kNoDoc;
+    for (uint32_t l = tid + kT; l < n_lists; l += kT) {  // further lists of this thread: read every round
+      unsigned long long key;
+      uint32_t doc;
+      if (!load_head(l, key, doc)) continue;
+      if (b_list == kNoDoc || beats(key, doc, b_key, b_doc)) {
+        b_key = key;
+        b_doc = doc;
+        b_list = l;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const unsigned long long o_key = __shfl_xor_sync(0xFFFFFFFFu, b_key, o);
+      const uint32_t o_doc = __shfl_xor_sync(0xFFFFFFFFu, b_doc, o), o_list = __shfl_xor_sync(0xFFFFFFFFu, b_list, o);
+      if (o_list != kNoDoc && (b_list == kNoDoc || beats(o_key, o_doc, b_key, b_doc))) {
+        b_key = o_key;
+        b_doc = o_doc;
+        b_list = o_list;
+      }
+    }
+    if (lane == 0) {
+      w_key[warp] = b_key;
+      w_doc[warp] = b_doc;
+      w_list[warp] = b_list;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long key = w_key[0];
+      uint32_t doc = w_doc[0], lst = w_list[0];
+      for (int w = 1; w < kT / 32; ++w)
+        if (w_list[w] != kNoDoc && (lst == kNoDoc || beats(w_key[w], w_doc[w], key, doc))) {
+          key = w_key[w];
+          doc = w_doc[w];
+          lst = w_list[w];
+        }
+      win_list = lst;
+      if (lst != kNoDoc) {
+        const size_t src = src_of(lst, head[lst]);
+        out_doc[(size_t)q * k + step] = doc;
+        out_final[(size_t)q * k + step] = in_final[src];
+        out_pr[(size_t)q * k + step] = in_pr[src];
+        head[lst] = head[lst] + 1;
+      }
+    }
+    __syncthreads();
+    const uint32_t wl = win_list;
+    if (wl == kNoDoc) break;  // every list is exhausted (uniform)
+    ++n_out;
+    if (wl == tid) c_valid = load_head(tid, c_key, c_doc);  // the owner refreshes its cached head
+  }
+  for (uint32_t j = n_out + tid; j < k; j += kT) {
     out_doc[(size_t)q * k + j] = kNoDoc;
     out_final[(size_t)q * k + j] = 0.0;
     out_pr[(size_t)q * k + j] = 0.0;
   }
-  __syncthreads();
-  for (uint32_t l = threadIdx.x; l < n_lists; l += kT) {
-    const uint32_t cnt = min(k, in_count[list_major ? (size_t)l * n_q + q : (size_t)q * n_lists + l]);
-    for (uint32_t j = 0; j < cnt; ++j) {
-      const size_t src = list_major ? ((size_t)l * n_q + q) * k + j : ((size_t)q * n_lists + l) * k + j;
-      const uint32_t d = in_doc[src];
-      if (d == kNoDoc) continue;
-      const uint32_t at = atomicAdd(&total, 1u);
-      key[at] = score_key(in_final[src]);
-      doc[at] = d;
-      from[at] = l * k + j;
-    }
-  }
-  __syncthreads();
-  const uint32_t nv = total;
-  (void)n;
-  for (uint32_t i = threadIdx.x; i < nv; i += kT) {
-    const unsigned long long ki = key[i];
-    const uint32_t di = doc[i];
-    uint32_t rank = 0;
-    for (uint32_t j = 0; j < nv; ++j) rank += beats(key[j], doc[j], ki, di) ? 1u : 0u;
-    if (rank < k) {
-      const uint32_t l = from[i] / k, jj = from[i] % k;
-      const size_t src = list_major ? ((size_t)l * n_q + q) * k + jj : ((size_t)q * n_lists + l) * k + jj;
-      out_doc[(size_t)q * k + rank] = di;
-      out_final[(size_t)q * k + rank] = in_final[src];
-      out_pr[(size_t)q * k + rank] = in_pr[src];
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) out_count[q] = min(total, k);
+  if (tid == 0) out_count[q] = n_out;
 }
 
 // Slab groups of every query: consecutive slabs are merged while their postings (all lists of the query)
@@ -1749,7 +1796,9 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   const uint64_t want_ctas = (uint64_t)e->sm_count * 16;
   n_slabs = std::max(n_slabs, (want_ctas + n_q - 1) / n_q);
   n_slabs = std::min<uint64_t>(n_slabs, n_sub);
-  n_slabs = std::min<uint64_t>(n_slabs, std::max<uint64_t>(1, (uint64_t)kMergeMax / k));
+  // per-slab partial lists: n_q * n_slabs * k entries of 20 bytes, kept under 16 GB
+  const uint64_t max_entries = std::max<uint64_t>(k, std::min<uint64_t>(kMergeMax, (16ull << 30) / (n_q * 20)));
+  n_slabs = std::min<uint64_t>(n_slabs, std::max<uint64_t>(1, max_entries / k));
   uint64_t sub_per_slab = (n_sub + n_slabs - 1) / n_slabs;
   // the impact-vector path keeps survivors as 16-bit slab offsets: slabs of <= 65536 docs when the merge allows
   // (with smaller slabs k_plan merges them back into 65536-doc ranges for that path).  Measured: 32768-doc
@@ -1759,7 +1808,7 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   if (const char* env = getenv("SS_SCORE_SLAB_DOCS")) slab_target = std::max<uint64_t>(kRange, strtoull(env, nullptr, 10));
   for (uint64_t t : {slab_target, (uint64_t)65536}) {
     const uint64_t spt = std::max<uint64_t>(1, t / kRange);
-    if (sub_per_slab > spt && (n_sub + spt - 1) / spt <= std::max<uint64_t>(1, (uint64_t)kMergeMax / k)) {
+    if (sub_per_slab > spt && (n_sub + spt - 1) / spt <= std::max<uint64_t>(1, max_entries / k)) {
       sub_per_slab = spt;
       break;
     }
@@ -1808,7 +1857,6 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
       if (!x) SS_CUDA(cudaEventCreate(&x));
   SS_CUDA(cudaFuncSetAttribute(k_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
   SS_CUDA(cudaFuncSetAttribute(k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  SS_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeMax * 16));
 
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[0], st));
   SS_CUDA(cudaMemcpyAsync(ws.kw_ptr.p, kw_ptr, (n_q + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -1915,7 +1963,7 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   if (n_ph) k_score<true><<<(unsigned)(n_q * n_slabs), kT, sizeof(Smem), st>>>(p);
   else k_score<false><<<(unsigned)(n_q * n_slabs), kT, sizeof(Smem), st>>>(p);
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[2], st));
-  k_merge<<<(unsigned)n_q, kT, (size_t)n_slabs * k * 16, st>>>((uint32_t)n_slabs, k, (uint32_t)n_q, 0, ws.part_doc.p,
+  k_merge<<<(unsigned)n_q, kT, (size_t)n_slabs * 2, st>>>((uint32_t)n_slabs, k, (uint32_t)n_q, 0, ws.part_doc.p,
                                                               ws.part_final.p, ws.part_pr.p, ws.part_count.p,
                                                               ws.out_doc.p, ws.out_final.p, ws.out_pr.p,
                                                               ws.out_count.p);
@@ -1973,8 +2021,7 @@ SS_API int ss_merge_topk(ss_engine* e, uint32_t n_lists, uint64_t n_q, uint32_t 
   SS_CUDA(cudaMemcpyAsync(d_fin.p, finals, n * 8, cudaMemcpyHostToDevice, st));
   SS_CUDA(cudaMemcpyAsync(d_pr.p, prs, n * 8, cudaMemcpyHostToDevice, st));
   SS_CUDA(cudaMemcpyAsync(d_cnt.p, counts, (size_t)n_lists * n_q * 4, cudaMemcpyHostToDevice, st));
-  SS_CUDA(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeMax * 16));
-  k_merge<<<(unsigned)n_q, kT, (size_t)n_lists * k * 16, st>>>(n_lists, k, (uint32_t)n_q, 1, d_doc.p, d_fin.p, d_pr.p,
+  k_merge<<<(unsigned)n_q, kT, (size_t)n_lists * 2, st>>>(n_lists, k, (uint32_t)n_q, 1, d_doc.p, d_fin.p, d_pr.p,
                                                               d_cnt.p, o_doc.p, o_fin.p, o_pr.p, o_cnt.p);
   SS_CUDA(cudaMemcpyAsync(out_doc, o_doc.p, n_q * k * 4, cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaMemcpyAsync(out_final, o_fin.p, n_q * k * 8, cudaMemcpyDeviceToHost, st));
