@@ -19,7 +19,11 @@
 // y_next once: the algorithmic bytes of SURVEY.md §8(d).
 //
 // Work split: rows with in-degree <= kShortMax are handled one per sub-warp
-// (LPR lanes, 16 bytes per lane); longer rows are cut into kChunk-edge tasks,
+// (LPR lanes, 16 bytes per lane) by one of three bit-identical kernels --
+// k_sweep_short32 (default: 32-bit padded row pointers, packed scale record, no
+// spills), k_sweep_short (first version; 64-bit-pointer fallback) and
+// k_sweep_short_async (opt-in: gathered rows land in a cp.async shared-memory
+// ring); longer rows are cut into kChunk-edge tasks,
 // one warp each, ordered by first source id so that concurrently running tasks
 // gather from neighbouring source ranges (L2 reuse); rows spanning several
 // tasks are finished by a fix-up pass that sums their partial rows in task
