@@ -162,7 +162,9 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr,
                           double* out_final, double* out_pr, uint32_t* out_count);
 
 /* Merge `n_lists` per-shard results of the same query batch ([n_q][k] each,
- * concatenated shard-major) into one [n_q][k] with the same comparator. */
+ * concatenated shard-major) into one [n_q][k] with the same comparator.  Each
+ * input list must be in ss_score_batch's output order (best first): this is a
+ * k-way merge.  n_lists * k <= 16384. */
 SS_API int ss_merge_topk(ss_engine* e, uint32_t n_lists, uint64_t n_q, uint32_t k,
                          const uint32_t* docs, const double* finals, const double* prs,
                          const uint32_t* counts, uint32_t* out_doc, double* out_final,
