@@ -1704,6 +1704,10 @@ static int build_dense_vectors(ss_engine* e, IndexState* ix, cudaStream_t st, ui
       std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
         return dfs[a] != dfs[b] ? dfs[a] > dfs[b] : terms[a] < terms[b];
       });
+      // the vectors may take at most a quarter of the device memory that is free now (2 bytes per doc and term)
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+        max_dense = (uint32_t)std::min<uint64_t>(max_dense, (free_b / 4) / (d_pad * 2));
       const uint32_t nd = std::min(n, max_dense);
       std::vector<uint32_t> chosen(nd);
       for (uint32_t i = 0; i < nd; ++i) chosen[i] = terms[order[i]];
