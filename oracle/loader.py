@@ -66,6 +66,8 @@ def lib():
                                          C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_int]
         L.oracle_score_batch.restype = C.c_int
+        L.oracle_score_batch_fair.argtypes = L.oracle_score_batch.argtypes
+        L.oracle_score_batch_fair.restype = C.c_int
         L.oracle_intersect.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
         L.oracle_intersect.restype = C.c_uint64
         _lib = L
@@ -180,8 +182,9 @@ class Table:
 
 
 def score_batch(title: Table, body: Table, n_docs, mag_title, mag_body, pagerank_m, kw_ptr, kw_terms,
-                ph_ptr=None, ph_terms=None, topic_probs=None, k=50, n_threads=0):
-    """retrieval.Retrieve's score/blend/top-k core -> (doc [Q][k], final, pr, count [Q])."""
+                ph_ptr=None, ph_terms=None, topic_probs=None, k=50, n_threads=0, fair=False):
+    """retrieval.Retrieve's score/blend/top-k core -> (doc [Q][k], final, pr, count [Q]).
+    fair=True: the same results from the CPU-friendly flavour (dense accumulators, all cores)."""
     mag_title = np.ascontiguousarray(mag_title, dtype=np.float64)
     mag_body = np.ascontiguousarray(mag_body, dtype=np.float64)
     kw_ptr = np.ascontiguousarray(kw_ptr, dtype=np.uint64)
@@ -202,10 +205,10 @@ def score_batch(title: Table, body: Table, n_docs, mag_title, mag_body, pagerank
     out_final = np.zeros((nq, k), dtype=np.float64)
     out_pr = np.zeros((nq, k), dtype=np.float64)
     out_count = np.zeros(nq, dtype=np.uint32)
-    rc = lib().oracle_score_batch(C.byref(title.c), C.byref(body.c), n_docs, _p(mag_title),
-                                  _p(mag_body), _p(pagerank_m), n_topics, nq, _p(kw_ptr),
-                                  _p(kw_terms), _p(ph_ptr), _p(ph_terms), _p(topic_probs), per_q, k,
-                                  _p(out_doc), _p(out_final), _p(out_pr), _p(out_count), n_threads)
+    fn = lib().oracle_score_batch_fair if fair else lib().oracle_score_batch
+    rc = fn(C.byref(title.c), C.byref(body.c), n_docs, _p(mag_title), _p(mag_body), _p(pagerank_m), n_topics, nq,
+            _p(kw_ptr), _p(kw_terms), _p(ph_ptr), _p(ph_terms), _p(topic_probs), per_q, k, _p(out_doc),
+            _p(out_final), _p(out_pr), _p(out_count), n_threads)
     assert rc == 0
     return out_doc, out_final, out_pr, out_count
 

@@ -532,3 +532,115 @@ extern "C" int oracle_score_batch(const oracle_table* title, const oracle_table*
   }
   return 0;
 }
+
+// "Fair" CPU flavour of oracle_score_batch (the same arithmetic on dense ids with the
+// data structures a CPU implementation would choose, all cores): per-thread dense accumulators instead of
+// a hash map per query, the blend term of a shared topic vector computed once per batch, a bounded
+// selection instead of sorting every hit.  Sums are formed in the same order (query tokens, body then
+// title postings, phrase last), so the results are the oracle's bit for bit.
+extern "C" int oracle_score_batch_fair(const oracle_table* title, const oracle_table* body, uint64_t n_docs,
+                                       const double* mag_title, const double* mag_body, const double* pagerank,
+                                       uint32_t n_topics, uint64_t n_q, const uint64_t* kw_ptr,
+                                       const uint32_t* kw_terms, const uint64_t* ph_ptr, const uint32_t* ph_terms,
+                                       const double* topic_probs, int probs_per_query, uint32_t k, uint32_t* out_doc,
+                                       double* out_final, double* out_pr, uint32_t* out_count, int n_threads) {
+  if (n_threads <= 0) n_threads = omp_get_max_threads();
+  std::vector<double> sqd_shared;
+  if (topic_probs && pagerank && !probs_per_query) {
+    sqd_shared.resize(n_docs);
+#pragma omp parallel for num_threads(n_threads) schedule(static)
+    for (uint64_t d = 0; d < n_docs; ++d) {
+      double s = 0.0;
+      for (uint32_t t = 0; t < n_topics; ++t) s += topic_probs[t] * pagerank[d * n_topics + t];
+      sqd_shared[d] = s;
+    }
+  }
+#pragma omp parallel num_threads(n_threads)
+  {
+    std::vector<double> acc_t(n_docs, 0.0), acc_b(n_docs, 0.0);
+    std::vector<uint8_t> seen(n_docs, 0);
+    std::vector<uint32_t> touched;
+    std::vector<Hit> best;
+#pragma omp for schedule(dynamic, 1)
+    for (uint64_t q = 0; q < n_q; ++q) {
+      const uint64_t kb = kw_ptr[q], ke = kw_ptr[q + 1];
+      const uint64_t pb = ph_ptr ? ph_ptr[q] : 0, pe = ph_ptr ? ph_ptr[q + 1] : 0;
+      touched.clear();
+      auto touch = [&](uint32_t d) {
+        if (!seen[d]) {
+          seen[d] = 1;
+          touched.push_back(d);
+        }
+      };
+      for (uint64_t i = kb; i < ke; ++i) {
+        uint64_t b, e;
+        table_range(body, kw_terms[i], &b, &e);
+        for (uint64_t p = b; p < e; ++p) {
+          const uint32_t d = body->doc_ids[p];
+          touch(d);
+          acc_b[d] += (double)body->w[p];
+        }
+        table_range(title, kw_terms[i], &b, &e);
+        for (uint64_t p = b; p < e; ++p) {
+          const uint32_t d = title->doc_ids[p];
+          touch(d);
+          acc_t[d] += (double)title->w[p];
+        }
+      }
+      if (pe > pb) {
+        std::unordered_map<uint32_t, std::pair<bool, float>> pt, pbod;
+        eval_phrase(title, body, ph_terms + pb, pe - pb, pt, pbod);
+        for (auto& kv : pbod) {
+          touch(kv.first);
+          acc_b[kv.first] += (double)kv.second.second;
+        }
+        for (auto& kv : pt) {
+          touch(kv.first);
+          acc_t[kv.first] += (double)kv.second.second;
+        }
+      }
+      const double* probs = topic_probs ? topic_probs + (probs_per_query ? q * n_topics : 0) : nullptr;
+      const double qmag = std::sqrt((double)((ke - kb) + (pe - pb)));
+      // bounded selection: keep the k best seen so far, worst of them at the heap's top
+      best.clear();
+      auto worse_first = [](const Hit& a, const Hit& b) { return hit_before(a, b); };  // heap top = last in order
+      for (uint32_t doc : touched) {
+        double sqd = 0.0;
+        if (probs && pagerank) {
+          if (!probs_per_query) sqd = sqd_shared[doc];
+          else
+            for (uint32_t t = 0; t < n_topics; ++t) sqd += probs[t] * pagerank[(uint64_t)doc * n_topics + t];
+        }
+        double br = acc_b[doc] / (mag_body[doc] * qmag);
+        double tr = acc_t[doc] / (mag_title[doc] * qmag);
+        if (std::isnan(br)) br = 0;
+        if (std::isnan(tr)) tr = 0;
+        acc_b[doc] = 0.0;
+        acc_t[doc] = 0.0;
+        seen[doc] = 0;
+        Hit h;
+        h.doc = doc;
+        h.pr = sqd;
+        h.final_rank = (0.33 * sqd + 0.38 * tr + 0.29 * br) * 100.0;
+        if (best.size() < k) {
+          best.push_back(h);
+          std::push_heap(best.begin(), best.end(), worse_first);
+        } else if (k && hit_before(h, best.front())) {
+          std::pop_heap(best.begin(), best.end(), worse_first);
+          best.back() = h;
+          std::push_heap(best.begin(), best.end(), worse_first);
+        }
+      }
+      std::sort(best.begin(), best.end(), hit_before);
+      const size_t keep = best.size();
+      out_count[q] = (uint32_t)keep;
+      for (uint32_t j = 0; j < k; ++j) {
+        const bool ok = j < keep;
+        out_doc[q * k + j] = ok ? best[j].doc : 0xFFFFFFFFu;
+        out_final[q * k + j] = ok ? best[j].final_rank : 0.0;
+        out_pr[q * k + j] = ok ? best[j].pr : 0.0;
+      }
+    }
+  }
+  return 0;
+}

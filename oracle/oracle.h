@@ -100,6 +100,14 @@ int oracle_score_batch(const oracle_table* title, const oracle_table* body, uint
                        const double* topic_probs, int probs_per_query, uint32_t k,
                        uint32_t* out_doc, double* out_final, double* out_pr, uint32_t* out_count,
                        int n_threads);
+/* same results, CPU-friendly data structures (dense accumulators, shared blend term, bounded selection) */
+int oracle_score_batch_fair(const oracle_table* title, const oracle_table* body, uint64_t n_docs,
+                       const double* mag_title, const double* mag_body, const double* pagerank,
+                       uint32_t n_topics, uint64_t n_q, const uint64_t* kw_ptr,
+                       const uint32_t* kw_terms, const uint64_t* ph_ptr, const uint32_t* ph_terms,
+                       const double* topic_probs, int probs_per_query, uint32_t k,
+                       uint32_t* out_doc, double* out_final, double* out_pr, uint32_t* out_count,
+                       int n_threads);
 
 /* retrieval/util.go:179-203 on its own (sorted multiset intersection). */
 uint64_t oracle_intersect(float* a, uint64_t na, float* b, uint64_t nb, float* out);

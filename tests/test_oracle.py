@@ -180,3 +180,26 @@ def test_blend_and_tie_order(built):
                                    topic_probs=probs2, k=10)
     assert d2[0].tolist() == d[0].tolist() and f2[0].tolist() == f[0].tolist()
     assert not np.array_equal(p2[0], p2[1])
+
+
+def test_score_batch_fair_flavour_is_identical(built):
+    # the CPU baseline's "fair" flavour (dense accumulators, shared blend term, bounded selection) must return
+    # exactly what the hash-map flavour returns: keyword + phrase queries, no blend / shared / per-query blend
+    from spaghettisearch_b200 import synth
+    V, D = 3000, 8000
+    t = synth.index_table(V, D, 0, with_positions=True)
+    b = synth.index_table(V, D, 1, with_positions=True)
+    wt, mt = O.term_weights(t.term_ptr, t.doc_ids, t.norm_tf, D, float(D))
+    wb, mb = O.term_weights(b.term_ptr, b.doc_ids, b.norm_tf, D, float(D))
+    ot, ob = O.Table(t.term_ptr, t.doc_ids, wt, t.pos_ptr, t.pos), O.Table(b.term_ptr, b.doc_ids, wb, b.pos_ptr, b.pos)
+    q = synth.queries(400, V, phrase_fraction=0.3, seed=51)
+    rng = np.random.default_rng(3)
+    pr = rng.uniform(0, 1e-4, (D, 16))
+    for probs in (None, np.full(16, 1 / 16), rng.dirichlet(np.ones(16), size=400)):
+        for k in (1, 10, 50):
+            a = O.score_batch(ot, ob, D, mt, mb, pr, q.kw_ptr, q.kw_terms, q.ph_ptr, q.ph_terms, topic_probs=probs, k=k)
+            f = O.score_batch(ot, ob, D, mt, mb, pr, q.kw_ptr, q.kw_terms, q.ph_ptr, q.ph_terms, topic_probs=probs, k=k,
+                              fair=True, n_threads=4)
+            assert np.array_equal(a[0], f[0]) and np.array_equal(a[3], f[3])
+            assert np.array_equal(a[1].view(np.uint64), f[1].view(np.uint64))
+            assert np.array_equal(a[2].view(np.uint64), f[2].view(np.uint64))
