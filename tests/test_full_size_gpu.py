@@ -83,17 +83,20 @@ def test_config2_scoring_full_size(engine):
     valid = docs != 0xFFFFFFFF
     sqd = pr @ probs
     assert np.allclose(prv[valid], sqd[docs[valid]], rtol=1e-12, atol=0)
-    # oracle on a sample of queries (bounded CPU time): identical ids/order, scores within 1e-6
+    # the oracle on EVERY query of the batch (its CPU-friendly flavour, bit-identical to the hash-map flavour --
+    # tests/test_oracle.py -- and fast enough for 4000 full-size queries): identical ids/order/counts,
+    # scores within 1e-6; plus the hash-map flavour itself on a few queries
     ot = O.Table(title.term_ptr, title.doc_ids, wt)
     ob = O.Table(body.term_ptr, body.doc_ids, wb)
-    sample = rng.choice(Q, 48, replace=False)
-    for qi in sample:
+    ref = O.score_batch(ot, ob, D, mt, mb, pr, q.kw_ptr, q.kw_terms, topic_probs=probs, k=K, fair=True)
+    assert np.array_equal(ref[3], count)
+    assert np.array_equal(ref[0], docs), np.argwhere(ref[0] != docs)[:5]
+    assert np.allclose(ref[1], final, rtol=1e-6, atol=0)
+    for qi in rng.choice(Q, 8, replace=False):
         a, b = int(q.kw_ptr[qi]), int(q.kw_ptr[qi + 1])
-        ref = O.score_batch(ot, ob, D, mt, mb, pr, np.array([0, b - a], np.uint64), q.kw_terms[a:b],
+        one = O.score_batch(ot, ob, D, mt, mb, pr, np.array([0, b - a], np.uint64), q.kw_terms[a:b],
                             topic_probs=probs, k=K, n_threads=1)
-        assert ref[3][0] == count[qi]
-        assert np.array_equal(ref[0][0], docs[qi])
-        assert np.allclose(ref[1][0], final[qi], rtol=1e-6, atol=0)
+        assert one[3][0] == count[qi] and np.array_equal(one[0][0], docs[qi])
     st = engine.score_stats()
     assert st.postings_scanned > 1e9 and st.docs_matched > 1e9
     engine.set_pagerank(None)
