@@ -109,6 +109,7 @@ typedef struct ss_pagerank_stats {
   double gather_ms_total;      /* device time of the two gather kernels only */
   double exchange_ms_total;    /* device time in the per-sweep NVLink exchange */
   double load_ms;              /* last ss_graph_load_csr, host wall clock */
+  double short_ms_total;       /* device time of the short-row kernel only (SS_FLAG_TIMING) */
 } ss_pagerank_stats;
 SS_API int ss_pagerank_get_stats(ss_engine* e, ss_pagerank_stats* out);
 
@@ -121,6 +122,12 @@ SS_API int ss_pagerank_get_stats(ss_engine* e, ss_pagerank_stats* out);
 SS_API int ss_index_load(ss_engine* e, int table, uint64_t n_terms, uint64_t n_docs,
                          const uint64_t* term_ptr, const uint32_t* doc_ids,
                          const float* norm_tf, const uint64_t* pos_ptr, const float* pos);
+
+/* Doc-sharded index: a shard loads its docs under shard-LOCAL ids 0 .. n_docs-1
+ * (doc_ids, norms and PageRank rows all local) and declares the global id of its local doc 0 here;
+ * ss_score_batch adds it to every doc id it returns.  Work per shard then depends on the shard's own
+ * size only.  Default 0. */
+SS_API int ss_index_set_doc_base(ss_engine* e, uint64_t doc_base);
 
 /* Drop both tables, their norms and the blend input (before loading another index). */
 SS_API int ss_index_clear(ss_engine* e);
@@ -161,10 +168,21 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr,
                           int32_t probs_per_query, uint32_t k, uint32_t* out_doc,
                           double* out_final, double* out_pr, uint32_t* out_count);
 
+/* The same call on a doc-sharded index (retrieval/main_retrieve.go:15-104 over all shards): every rank of
+ * the ss_comm_init group passes the SAME query batch, scores it against its shard, all-gathers the local
+ * top-k lists over NCCL and merges them on its own stream with the same comparator, so every rank
+ * returns the global result (doc ids global via ss_index_set_doc_base).  With no communicator it is
+ * ss_score_batch.  world * k <= 16384. */
+SS_API int ss_score_batch_sharded(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr,
+                                  const uint32_t* kw_terms, const uint64_t* ph_ptr,
+                                  const uint32_t* ph_terms, const double* topic_probs,
+                                  int32_t probs_per_query, uint32_t k, uint32_t* out_doc,
+                                  double* out_final, double* out_pr, uint32_t* out_count);
+
 /* Merge `n_lists` per-shard results of the same query batch ([n_q][k] each,
  * concatenated shard-major) into one [n_q][k] with the same comparator.  Each
  * input list must be in ss_score_batch's output order (best first): this is a
- * k-way merge.  n_lists * k <= 16384. */
+ * k-way merge.  k <= 128 and n_lists * k <= 16384. */
 SS_API int ss_merge_topk(ss_engine* e, uint32_t n_lists, uint64_t n_q, uint32_t k,
                          const uint32_t* docs, const double* finals, const double* prs,
                          const uint32_t* counts, uint32_t* out_doc, double* out_final,
@@ -179,6 +197,8 @@ typedef struct ss_score_stats {
   uint32_t launches;           /* kernels launched by the last ss_score_batch */
   double kernel_ms;            /* device time of the last batch (SS_FLAG_TIMING) */
   double score_kernel_ms;      /* device time of the dominant scoring kernel */
+  double shard_merge_ms;       /* device time from the end of the local merge to the end of the result copies
+                                  (ss_score_batch_sharded: NCCL all-gather + cross-shard merge + D2H) */
 } ss_score_stats;
 SS_API int ss_score_get_stats(ss_engine* e, ss_score_stats* out);
 

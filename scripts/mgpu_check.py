@@ -36,28 +36,38 @@ if rank == 0:
           "exchange ms/sweep", st.exchange_ms_total / max(1, st.sweeps), flush=True)
     assert sum(int(a[0]) for a in allrows) == N and sum(int(a[1]) for a in allrows) == int(row_ptr[-1])
 
-# ---- HP-2: doc-sharded index, global df, merge
+# ---- HP-2: doc-sharded index under shard-local doc ids, global df, cross-shard merge inside the engine
 V, D, Q, K = 5000, 40000, 500, 10
 dlo, dhi = sharding.doc_shard(rank, world, D)
+rng = np.random.default_rng(17)
+pr = rng.random((D, 16)) * 1e-4          # forw[3] rows, same on every rank
+probs = np.full(16, 1.0 / 16)
+eng.index_set_doc_base(dlo)
 for tid in (capi.SS_TITLE, capi.SS_BODY):
     t = synth.index_table(V, D, tid, doc_lo=dlo, doc_hi=dhi, with_positions=True, n_threads=4)
-    eng.index_load(tid, D, t.term_ptr, t.doc_ids, t.norm_tf, t.pos_ptr, t.pos)
-    eng.term_weights(tid, float(D), t.n_postings, D, df_global=t.df_global, want=False)
+    eng.index_load(tid, dhi - dlo, t.term_ptr, t.doc_ids - np.uint32(dlo), t.norm_tf, t.pos_ptr, t.pos)
+    eng.term_weights(tid, float(D), t.n_postings, dhi - dlo, df_global=t.df_global, want=False)
+eng.set_pagerank(pr[dlo:dhi])
 q = synth.queries(Q, V, phrase_fraction=0.25, seed=44)
-local_res = eng.score_batch(q.kw_ptr, q.kw_terms, q.ph_ptr, q.ph_terms, k=K)
+merged = eng.score_batch(q.kw_ptr, q.kw_terms, q.ph_ptr, q.ph_terms, topic_probs=probs, k=K, sharded=True)
+# the round-1 route (per-shard lists gathered by the harness, ss_merge_topk on rank 0) must agree
+local_res = eng.score_batch(q.kw_ptr, q.kw_terms, q.ph_ptr, q.ph_terms, topic_probs=probs, k=K)
 docs, finals, prs, counts = sharding.gather_result_lists(*local_res, device="cuda")
 ok_sc = True
+ft = synth.index_table(V, D, 0, with_positions=True, n_threads=4)
+fb = synth.index_table(V, D, 1, with_positions=True, n_threads=4)
+wt, mt = O.term_weights(ft.term_ptr, ft.doc_ids, ft.norm_tf, D, float(D))
+wb, mb = O.term_weights(fb.term_ptr, fb.doc_ids, fb.norm_tf, D, float(D))
+exp = O.score_batch(O.Table(ft.term_ptr, ft.doc_ids, wt, ft.pos_ptr, ft.pos),
+                    O.Table(fb.term_ptr, fb.doc_ids, wb, fb.pos_ptr, fb.pos), D, mt, mb, pr, q.kw_ptr,
+                    q.kw_terms, q.ph_ptr, q.ph_terms, topic_probs=probs, k=K, n_threads=4)
+ok_sc = (np.array_equal(merged[0], exp[0]) and np.array_equal(merged[3], exp[3]) and
+         np.allclose(merged[1], exp[1], rtol=1e-6, atol=0) and np.allclose(merged[2], exp[2], rtol=1e-6, atol=0))
 if rank == 0:
-    merged = eng.merge_topk(docs, finals, prs, counts)
-    ft = synth.index_table(V, D, 0, with_positions=True, n_threads=4)
-    fb = synth.index_table(V, D, 1, with_positions=True, n_threads=4)
-    wt, mt = O.term_weights(ft.term_ptr, ft.doc_ids, ft.norm_tf, D, float(D))
-    wb, mb = O.term_weights(fb.term_ptr, fb.doc_ids, fb.norm_tf, D, float(D))
-    exp = O.score_batch(O.Table(ft.term_ptr, ft.doc_ids, wt, ft.pos_ptr, ft.pos),
-                        O.Table(fb.term_ptr, fb.doc_ids, wb, fb.pos_ptr, fb.pos), D, mt, mb, None, q.kw_ptr,
-                        q.kw_terms, q.ph_ptr, q.ph_terms, k=K, n_threads=8)
-    ok_sc = (np.array_equal(merged[0], exp[0]) and np.array_equal(merged[3], exp[3]) and
-             np.allclose(merged[1], exp[1], rtol=1e-6, atol=0))
+    m2 = eng.merge_topk(docs, finals, prs, counts)
+    ok_sc = ok_sc and all(np.array_equal(a, b) for a, b in zip(m2, merged))
+    print("sharded scoring: merged top-k", "identical" if ok_sc else "DIFFERS", "shard_merge_ms",
+          eng.score_stats().shard_merge_ms, flush=True)
 flag = torch.tensor([int(ok_pr and ok_sc)], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 eng.close()

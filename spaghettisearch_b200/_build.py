@@ -68,16 +68,26 @@ def gpu_sources():
 
 
 def build_gpu(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> Path:
-    """Compile every .cu under csrc/ for sm_100a into one shared library."""
+    """Compile every .cu under csrc/ for sm_100a (one object per file, in parallel) into one shared library."""
+    from concurrent.futures import ThreadPoolExecutor
     cu, hdr = gpu_sources()
-    if force or _stale(GPU_LIB, cu + hdr):
-        cmd = [_nvcc(), *NVCC_ARCH, "-O3", "-std=c++17", "-lineinfo", "-shared",
-               "-Xcompiler", "-fPIC,-Wall,-fvisibility=hidden", "-I", ROOT / "include", "-I", CSRC,
-               "-ccbin", _host_cxx()]
-        if ptxas_info:
-            cmd += ["-Xptxas", "-v"]
-        cmd += ["-o", GPU_LIB, *cu, "-ldl"]
-        _run(cmd, verbose)
+    if not (force or _stale(GPU_LIB, cu + hdr)):
+        return GPU_LIB
+    obj_dir = PKG / "_obj"
+    obj_dir.mkdir(exist_ok=True)
+    base = [_nvcc(), *NVCC_ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-fvisibility=hidden",
+            "-I", ROOT / "include", "-I", CSRC, "-ccbin", _host_cxx()]
+    if ptxas_info:
+        base += ["-Xptxas", "-v"]
+    objs, jobs = [], []
+    for src in cu:
+        obj = obj_dir / (src.stem + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [src] + hdr):
+            jobs.append(base + ["-c", "-o", obj, src])
+    with ThreadPoolExecutor(max_workers=max(1, len(jobs))) as pool:
+        list(pool.map(lambda c: _run(c, verbose), jobs))
+    _run([_nvcc(), *NVCC_ARCH, "-shared", "-ccbin", _host_cxx(), "-o", GPU_LIB, *objs, "-ldl"], verbose)
     return GPU_LIB
 
 

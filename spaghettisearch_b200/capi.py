@@ -21,7 +21,7 @@ SS_FLAG_TIMING = 1
 EXPORTS = [
     "ss_version", "ss_create", "ss_destroy", "ss_last_error", "ss_stream_handle", "ss_comm_unique_id", "ss_comm_init",
     "ss_graph_load_csr", "ss_pagerank", "ss_pagerank_fetch", "ss_pagerank_get_stats", "ss_index_load",
-    "ss_index_clear",
+    "ss_index_clear", "ss_index_set_doc_base", "ss_score_batch_sharded",
     "ss_term_weights", "ss_set_doc_norms", "ss_set_pagerank", "ss_use_pagerank", "ss_score_batch",
     "ss_merge_topk", "ss_score_get_stats",
 ]
@@ -41,13 +41,13 @@ class PagerankStats(C.Structure):
     _fields_ = [("n_nodes", C.c_uint64), ("n_edges", C.c_uint64), ("row_lo", C.c_uint64), ("local_rows", C.c_uint64),
                 ("local_edges", C.c_uint64), ("sweeps", C.c_uint32), ("launches", C.c_uint32),
                 ("sweep_ms_total", C.c_double), ("gather_ms_total", C.c_double),
-                ("exchange_ms_total", C.c_double), ("load_ms", C.c_double)]
+                ("exchange_ms_total", C.c_double), ("load_ms", C.c_double), ("short_ms_total", C.c_double)]
 
 
 class ScoreStats(C.Structure):
     _fields_ = [("postings_scanned", C.c_uint64), ("docs_matched", C.c_uint64),
                 ("algorithmic_bytes", C.c_uint64), ("launches", C.c_uint32), ("kernel_ms", C.c_double),
-                ("score_kernel_ms", C.c_double)]
+                ("score_kernel_ms", C.c_double), ("shard_merge_ms", C.c_double)]
 
 
 _lib = None
@@ -89,6 +89,8 @@ def load():
     L.ss_set_pagerank.argtypes = [vp, u64, u32, vp]
     L.ss_use_pagerank.argtypes = [vp]
     L.ss_score_batch.argtypes = [vp, u64, vp, vp, vp, vp, vp, i32, u32, vp, vp, vp, vp]
+    L.ss_score_batch_sharded.argtypes = [vp, u64, vp, vp, vp, vp, vp, i32, u32, vp, vp, vp, vp]
+    L.ss_index_set_doc_base.argtypes = [vp, u64]
     L.ss_merge_topk.argtypes = [vp, u32, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ss_score_get_stats.argtypes = [vp, C.POINTER(ScoreStats)]
     for name in EXPORTS:
@@ -205,6 +207,9 @@ class Engine:
     def index_clear(self):
         self._check(self.L.ss_index_clear(self.h))
 
+    def index_set_doc_base(self, doc_base: int):
+        self._check(self.L.ss_index_set_doc_base(self.h, int(doc_base)))
+
     def term_weights(self, table, total_docs, n_postings, n_docs, df_global=None, want=True):
         df_global = _as(df_global, np.uint64)
         w = np.zeros(n_postings, dtype=np.float32) if want else None
@@ -226,8 +231,10 @@ class Engine:
     def use_pagerank(self):
         self._check(self.L.ss_use_pagerank(self.h))
 
-    def score_batch(self, kw_ptr, kw_terms, ph_ptr=None, ph_terms=None, topic_probs=None, k=50, out=None):
-        """-> (doc [Q][k] uint32, final [Q][k], pr [Q][k], count [Q])."""
+    def score_batch(self, kw_ptr, kw_terms, ph_ptr=None, ph_terms=None, topic_probs=None, k=50, out=None,
+                    sharded=False):
+        """-> (doc [Q][k] uint32, final [Q][k], pr [Q][k], count [Q]).  sharded: ss_score_batch_sharded
+        (every rank of the communicator calls it with the same batch and gets the global top-k)."""
         kw_ptr, kw_terms = _as(kw_ptr, np.uint64), _as(kw_terms, np.uint32)
         ph_ptr, ph_terms = _as(ph_ptr, np.uint64), _as(ph_terms, np.uint32)
         nq = len(kw_ptr) - 1
@@ -238,9 +245,9 @@ class Engine:
         if out is None:
             out = (np.zeros((nq, k), dtype=np.uint32), np.zeros((nq, k), dtype=np.float64),
                    np.zeros((nq, k), dtype=np.float64), np.zeros(nq, dtype=np.uint32))
-        self._check(self.L.ss_score_batch(self.h, nq, _ptr(kw_ptr), _ptr(kw_terms), _ptr(ph_ptr), _ptr(ph_terms),
-                                          _ptr(topic_probs), per_q, k, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
-                                          _ptr(out[3])))
+        fn = self.L.ss_score_batch_sharded if sharded else self.L.ss_score_batch
+        self._check(fn(self.h, nq, _ptr(kw_ptr), _ptr(kw_terms), _ptr(ph_ptr), _ptr(ph_terms),
+                _ptr(topic_probs), per_q, k, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3])))
         return out
 
     def merge_topk(self, docs, finals, prs, counts):

@@ -15,3 +15,5 @@ int comm_allgatherv_bytes(ss_engine* e, void* dev_buf, const size_t* byte_off, c
 // every rank contributes `bytes` bytes; out receives world * bytes (host buffers, small payloads:
 // staged through device memory and NCCL)
 int comm_allgather_host_bytes(ss_engine* e, const void* in, size_t bytes, void* out);
+// n equally sized device blocks per rank: out[i] receives world * bytes[i] (rank-major), one NCCL group
+int comm_allgather_dev(ss_engine* e, int n, const void* const* in, void* const* out, const size_t* bytes);

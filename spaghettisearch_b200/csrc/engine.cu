@@ -105,12 +105,37 @@ int comm_allgatherv_bytes(ss_engine* e, void* dev_buf, const size_t* byte_off, c
   auto* api = ss::nccl_api();
   SS_REQUIRE(api, SS_ERR_NCCL, "libnccl not loadable");
   SS_NCCL(api, api->GroupStart());
+  ncclResult_t first = ncclSuccess;
   for (int r = 0; r < e->comm->world; ++r) {
     if (byte_cnt[r] == 0) continue;
     char* p = (char*)dev_buf + byte_off[r];
-    SS_NCCL(api, api->Broadcast(p, p, byte_cnt[r], ncclChar, r, e->comm->comm, e->stream));
+    const ncclResult_t rc = api->Broadcast(p, p, byte_cnt[r], ncclChar, r, e->comm->comm, e->stream);
+    if (rc != ncclSuccess && first == ncclSuccess) first = rc;
   }
-  SS_NCCL(api, api->GroupEnd());
+  const ncclResult_t end = api->GroupEnd();  // always closed, also on the error path
+  SS_NCCL(api, first);
+  SS_NCCL(api, end);
+  return SS_OK;
+}
+
+int comm_allgather_dev(ss_engine* e, int n, const void* const* in, void* const* out, const size_t* bytes) {
+  if (!e->comm || e->comm->world == 1) {
+    for (int i = 0; i < n; ++i)
+      if (bytes[i]) SS_CUDA(cudaMemcpyAsync(out[i], in[i], bytes[i], cudaMemcpyDeviceToDevice, e->stream));
+    return SS_OK;
+  }
+  auto* api = ss::nccl_api();
+  SS_REQUIRE(api && api->AllGather, SS_ERR_NCCL, "libnccl not loadable");
+  SS_NCCL(api, api->GroupStart());
+  ncclResult_t first = ncclSuccess;
+  for (int i = 0; i < n; ++i) {
+    if (!bytes[i]) continue;
+    const ncclResult_t r = api->AllGather(in[i], out[i], bytes[i], ncclChar, e->comm->comm, e->stream);
+    if (r != ncclSuccess && first == ncclSuccess) first = r;
+  }
+  const ncclResult_t end = api->GroupEnd();  // always closed, also on the error path
+  SS_NCCL(api, first);
+  SS_NCCL(api, end);
   return SS_OK;
 }
 

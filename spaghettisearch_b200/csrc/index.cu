@@ -214,7 +214,21 @@ SS_API int ss_index_load(ss_engine* e, int table, uint64_t n_terms, uint64_t n_d
     return SS_ERR_INVALID;
   }
   tb.loaded = true;
+  // everything derived from the doc id space, the weights or the norms is stale now
   ix->dense_valid = false;
+  ix->sqd_valid = false;
+  ix->meta32_valid = false;
+  ix->zvec_valid = false;
+  return SS_OK;
+}
+
+SS_API int ss_index_set_doc_base(ss_engine* e, uint64_t doc_base) {
+  SS_REQUIRE(e, SS_ERR_INVALID, "ss_index_set_doc_base: engine is NULL");
+  SS_REQUIRE(doc_base < 0xFFFFFFFFull, SS_ERR_INVALID, "ss_index_set_doc_base: doc ids are 32 bit");
+  std::lock_guard<std::mutex> lock(e->mu);
+  IndexState* ix = index_state(e);
+  SS_REQUIRE(ix, SS_ERR_OOM, "host allocation failed");
+  ix->doc_base = doc_base;
   return SS_OK;
 }
 

@@ -27,7 +27,8 @@ struct TableState {
 };
 
 struct IndexState {
-  uint64_t D = 0;  // doc id space
+  uint64_t D = 0;  // doc id space (shard-local ids 0 .. D-1)
+  uint64_t doc_base = 0;  // global id of local doc 0 (doc-sharded index): added to the ids ss_score_batch returns
   TableState tab[2];
   // forw[3] rows for the blend
   uint32_t T = 0;
@@ -63,7 +64,10 @@ struct IndexState {
     ss::DevBuf<double> probs, part_final, part_pr, out_final, out_pr, zero_mag;
     ss::DevBuf<unsigned long long> stats, qthr;
     ss::DevBuf<uint8_t> group_len;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // cross-shard gather of ss_score_batch_sharded: [world][n_q][k] lists and [world][n_q] counts
+    ss::DevBuf<uint32_t> all_doc, all_count, loc_doc, loc_count;
+    ss::DevBuf<double> all_final, all_pr, loc_final, loc_pr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     ~Workspace() {
       for (auto& e : ev)
         if (e) cudaEventDestroy(e);

@@ -1018,7 +1018,7 @@ struct PagerankState {
   ss::DevBuf<double> mul, partials, red, stage, sums, tot, init, out_stage[2];
   bool have_result = false;
   ss_pagerank_stats stats{};
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [4]: end of the short-row kernel
   cudaEvent_t out_ev[2] = {nullptr, nullptr};
   // fused exchange over peer memory (CUDA IPC): peers' y[0]/y[1]
   bool fused = false;
@@ -1342,7 +1342,7 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
   s->have_result = false;
   s->stats.sweeps = 0;
   s->stats.launches = 0;
-  s->stats.sweep_ms_total = s->stats.gather_ms_total = s->stats.exchange_ms_total = 0;
+  s->stats.sweep_ms_total = s->stats.gather_ms_total = s->stats.exchange_ms_total = s->stats.short_ms_total = 0;
   if (n_topics == 0) {  // empty forw[5]: every node gets {} (pagerank.go:53-63)
     s->T = 0;
     s->have_result = true;
@@ -1507,6 +1507,7 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
       } else {
         k_sweep_short<L, V><<<grid_short, kThreads, 0, st>>>(q, n_row_blocks);
       }
+      if (timing) cudaEventRecord(s->ev[4], st);
       q.red = s->red.p + (size_t)grid_short * W;
       k_sweep_long<L, V><<<grid_long, kThreads, 0, st>>>(q, s->tasks.p, s->n_tasks, s->partials.p);
       if (timing) cudaEventRecord(s->ev[1], st);
@@ -1537,6 +1538,8 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
       s->stats.sweep_ms_total += ms;
       cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]);
       s->stats.gather_ms_total += ms;
+      cudaEventElapsedTime(&ms, s->ev[0], s->ev[4]);
+      s->stats.short_ms_total += ms;
       cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]);
       s->stats.exchange_ms_total += ms;
     }

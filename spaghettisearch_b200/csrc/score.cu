@@ -24,6 +24,7 @@
 
 #include <cuda_fp16.h>
 
+#include "comm.cuh"
 #include "index.cuh"
 
 namespace {
@@ -32,9 +33,6 @@ constexpr int kT = 256;        // threads per CTA
 constexpr int kRange = 2048;   // docs per sub-range
 constexpr int kCand = 1024;    // candidate buffer = doc slots finished per round
 constexpr int kMaxK = 128;
-constexpr int kMaxKw = 64;     // keyword tokens per query handled in-kernel
-constexpr int kMaxPh = 32;     // phrase tokens per query handled in-kernel
-constexpr int kMaxLists = 2 * (kMaxKw + kMaxPh);
 constexpr int kBounds = 4096;   // sub-range boundary table entries per pass
 constexpr uint32_t kNoDoc = 0xFFFFFFFFu;
 constexpr int kDenseRange = 4096;  // docs per sub-range of the impact-vector path
@@ -116,1252 +114,29 @@ __device__ __forceinline__ uint64_t lower_bound_doc(const uint32_t* __restrict__
   return lo;
 }
 
-struct Smem {
-  double acc[2][kRange];        // [0] TitleRank, [1] BodyRank sums of the sub-range
-  unsigned long long cand_key[kCand];
-  unsigned long long top_key[2][kMaxK];
-  unsigned long long cur[kMaxLists], hi[kMaxLists];  // current sub-range of every list
-  unsigned long long base[kMaxLists];               // start of the list inside the slab
-  uint32_t len[kMaxLists];                          // postings of the list inside the slab
-  uint32_t bounds[kBounds];                         // [list][sub-range] offsets from base
-  uint32_t cand_doc[kCand];
-  uint32_t top_doc[2][kMaxK];
-  uint32_t bits[kRange / 32];
-  uint32_t dbits[kDenseRange / 32];  // impact-vector path: docs with a sparse-token posting
-  uint16_t mlist[kRange];  // slots of the sub-range's matched docs, in first-touch order
-  uint32_t n_cand, n_ent, n_list, top_n, top_buf;
-  unsigned long long thr_key, piv_key;
-  uint32_t thr_doc, piv_doc;
-  float thr_f;  // fp32 lower bound of the score a doc needs: max(local k-th best, the query's running bound)
-  unsigned long long gkey;  // the query's running bound (score key of some slab's k-th best), 0 = none
-  float gthr_f;             // its score rounded down to fp32 (-inf when none)
-  uint8_t tok_dense[kMaxKw + kMaxPh];   // dense slot of every token, keyword then phrase (255 = sparse)
-  uint8_t dense_slots[kMaxKw + kMaxPh]; // the dense tokens' slots, in token order
-  uint8_t sparse_toks[kMaxKw + kMaxPh]; // indices of the sparse tokens
-  uint32_t n_dense_tok, n_sparse_tok, n_dense_kw;
-  float zred[kT / 32];
-};
-
-// Union of the running top-k and the candidate buffer -> new running top-k by
-// counting, for each element, how many others beat it (elements are distinct
-// in (key, doc), so ranks are a permutation).  A large candidate set is first
-// thinned with a pivot: the k-th best of a kSample-element sample is beaten by
-// at most k-1 sample members, so every candidate the pivot beats is outside
-// the top k and can be dropped without changing the result.
-constexpr uint32_t kSample = 128;
-__device__ void merge_candidates(Smem& s, uint32_t k) {
-  if (s.n_cand > 2 * kSample && 4 * k <= kSample) {
-    const uint32_t nc0 = s.n_cand;
-    if (threadIdx.x < kSample) {
-      const unsigned long long ki = s.cand_key[threadIdx.x];
-      const uint32_t di = s.cand_doc[threadIdx.x];
-      uint32_t rank = 0;
-      for (uint32_t j = 0; j < kSample; ++j) rank += beats(s.cand_key[j], s.cand_doc[j], ki, di) ? 1u : 0u;
-      if (rank == k - 1) {
-        s.piv_key = ki;
-        s.piv_doc = di;
-      }
-    }
-    // survivors are re-packed: read into registers, barrier, write
-    constexpr int kPerThread = kCand / kT;
-    unsigned long long rk[kPerThread];
-    uint32_t rd[kPerThread];
-#pragma unroll
-    for (int c = 0; c < kPerThread; ++c) {
-      const uint32_t i = threadIdx.x + c * kT;
-      rk[c] = i < nc0 ? s.cand_key[i] : 0ull;
-      rd[c] = i < nc0 ? s.cand_doc[i] : kNoDoc;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s.n_cand = 0;
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < kPerThread; ++c) {
-      const uint32_t i = threadIdx.x + c * kT;
-      if (i < nc0 && !beats(s.piv_key, s.piv_doc, rk[c], rd[c])) {
-        const uint32_t j = atomicAdd(&s.n_cand, 1u);
-        s.cand_key[j] = rk[c];
-        s.cand_doc[j] = rd[c];
-      }
-    }
-    __syncthreads();
-  }
-  const uint32_t nt = s.top_n, nc = s.n_cand, n = nt + nc;
-  const uint32_t ob = s.top_buf, nb = ob ^ 1;
-  for (uint32_t i = threadIdx.x; i < n; i += kT) {
-    const unsigned long long ki = i < nt ? s.top_key[ob][i] : s.cand_key[i - nt];
-    const uint32_t di = i < nt ? s.top_doc[ob][i] : s.cand_doc[i - nt];
-    uint32_t rank = 0;
-    for (uint32_t j = 0; j < nt; ++j) rank += beats(s.top_key[ob][j], s.top_doc[ob][j], ki, di) ? 1u : 0u;
-    for (uint32_t j = 0; j < nc; ++j) rank += beats(s.cand_key[j], s.cand_doc[j], ki, di) ? 1u : 0u;
-    if (rank < k) {
-      s.top_key[nb][rank] = ki;
-      s.top_doc[nb][rank] = di;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    s.top_n = min(k, n);
-    s.top_buf = nb;
-    s.n_cand = 0;
-    if (s.top_n == k) {
-      s.thr_key = s.top_key[nb][k - 1];
-      s.thr_doc = s.top_doc[nb][k - 1];
-      const double thr = key_score(s.thr_key);
-      // NaN as k-th best (only NaN scores so far) must not filter anything
-      s.thr_f = isnan(thr) ? s.gthr_f : fmaxf(s.gthr_f, __double2float_rd(thr));
-    }
-  }
-  __syncthreads();
-}
-
-// Sort-path entry: doc offset in the slab (24 bits) | list sequence (8) | weight bits (32).
-// Sorting the 64-bit keys groups a doc's weights in query-token order.
-constexpr uint32_t kSortMax = 2 * kRange;  // entries; the buffer aliases the two accumulator arrays
-__device__ __forceinline__ unsigned long long make_entry(uint32_t off, uint32_t seq, float w) {
-  return ((unsigned long long)off << 40) | ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(w);
-}
-
-// First posting to touch a doc slot of the sub-range appends it to the matched list, so that the
-// finalize step costs what the matches cost (the first version walked the whole bitmap: ~760
-// warp instructions per warp and sub-range whatever the density, the dominant cost for all but
-// the densest lists).
-__device__ __forceinline__ void mark_matched(Smem& s, uint32_t slot) {
-  const uint32_t bit = 1u << (slot & 31);
-  const uint32_t old = atomicOr(&s.bits[slot >> 5], bit);
-  if (!(old & bit)) s.mlist[atomicAdd(&s.n_list, 1u) & (kRange - 1)] = (uint16_t)slot;
-}
-
-// phrase.go:53-109 for one table over the lists' current ranges [cur, hi).  Lists
-// l0+2*i+tb hold token i.  A doc gets ONE weight = fp32 sum of the tokens' weights
-// in phrase order iff every token has a posting in this table and some position a
-// of token 0 has a + i among token i's positions (compared as
-// (pos_i - float32(i)) == pos_0, phrase.go:144-146, util.go:185).
-// EMIT = false: add into the sub-range accumulators; EMIT = true: append a sort entry.
-template <int EMIT>
-__device__ void apply_phrase(const ScoreParams& p, Smem& s, int tb, uint32_t l0, uint32_t L, uint64_t d0,
-                             uint32_t seq, unsigned long long& n_postings) {
-  const TableView& tv = p.tab[tb];
-  uint32_t drv = 0;
-  unsigned long long best = ~0ull;
-  for (uint32_t i = 0; i < L; ++i) {
-    const uint32_t l = l0 + 2 * i + tb;
-    const unsigned long long len = s.hi[l] - s.cur[l];
-    if (len == 0) return;  // a token without postings here: nothing can match (uniform across the CTA)
-    if (len < best) {
-      best = len;
-      drv = i;
-    }
-  }
-  const uint32_t ld = l0 + 2 * drv + tb;
-  for (unsigned long long q = s.cur[ld] + threadIdx.x; q < s.hi[ld]; q += kT) {
-    const uint32_t doc = tv.doc_ids[q];
-    unsigned long long pi[kMaxPh];
-    bool all = true;
-    for (uint32_t i = 0; i < L && all; ++i) {
-      if (i == drv) {
-        pi[i] = q;
-        continue;
-      }
-      const uint32_t l = l0 + 2 * i + tb;
-      unsigned long long a = s.cur[l], b = s.hi[l];
-      while (a < b) {
-        const unsigned long long mid = (a + b) >> 1;
-        if (tv.doc_ids[mid] < doc) a = mid + 1; else b = mid;
-      }
-      if (a < s.hi[l] && tv.doc_ids[a] == doc) pi[i] = a; else all = false;
-    }
-    n_postings += L;
-    if (!all) continue;
-    bool hit = false;
-    if (tv.pos_ptr) {
-      const unsigned long long a0 = tv.pos_ptr[pi[0]], a1 = tv.pos_ptr[pi[0] + 1];
-      for (unsigned long long x = a0; x < a1 && !hit; ++x) {
-        const float a = __fadd_rn(tv.pos[x], -0.0f);
-        bool ok = true;
-        for (uint32_t i = 1; i < L && ok; ++i) {
-          const float shift = (float)(uint8_t)i;
-          bool found = false;
-          for (unsigned long long y = tv.pos_ptr[pi[i]]; y < tv.pos_ptr[pi[i] + 1] && !found; ++y)
-            found = __fadd_rn(tv.pos[y], -shift) == a;
-          ok = found;
-        }
-        hit = ok;
-      }
-    }
-    if (!hit) continue;
-    float sum = 0.0f;  // phrase.go:59,69,83: float32 running sum in token order
-    for (uint32_t i = 0; i < L; ++i) sum = __fadd_rn(sum, tv.w[pi[i]]);
-    const uint32_t slot = (uint32_t)(doc - d0);
-    if (EMIT == 1) {
-      unsigned long long* ent = reinterpret_cast<unsigned long long*>(&s.acc[0][0]);
-      ent[atomicAdd(&s.n_ent, 1u)] = make_entry(slot, seq, sum);
-    } else if (EMIT == 2) {  // lookup path: (doc offset, weight) appended from position `seq` of its arrays
-      const uint32_t at = seq + atomicAdd(&s.n_ent, 1u);
-      reinterpret_cast<uint32_t*>(&s.acc[0][0])[at] = slot;
-      reinterpret_cast<float*>(&s.acc[1][0])[at] = sum;
-    } else {
-      s.acc[tb][slot] = __dadd_rn(s.acc[tb][slot], (double)sum);
-      mark_matched(s, slot);
-    }
-  }
-}
-
-// Exact per-doc inputs of the final rank (only docs that survive the screening need them).
-struct DocMeta {
-  double mag_t, mag_b, sqd;
-};
-__device__ __forceinline__ DocMeta load_meta(const ScoreParams& p, uint32_t q, uint64_t doc) {
-  DocMeta m;
-  m.mag_b = p.mag[1][doc];
-  m.mag_t = p.mag[0][doc];
-  m.sqd = 0.0;  // get_metadata.go:39-42
-  if (p.sqd) {
-    m.sqd = p.sqd[doc];
-  } else if (p.probs) {
-    const double* pr = p.pr + doc * p.T;
-    const double* pq = p.probs + (uint64_t)q * p.T;
-    for (uint32_t t = 0; t < p.T; ++t) m.sqd = __dadd_rn(m.sqd, __dmul_rn(pq[t], pr[t]));
-  }
-  return m;
-}
-
-// cosine, NaN -> 0, PageRank blend (get_metadata.go:53-69); a doc that can still
-// make the top k goes to the candidate buffer.
-//
-// Screening first: once k results exist, a doc whose score -- bounded from one packed fp32
-// record (reciprocal norms, blend bound) with a margin far above fp32 rounding -- stays below
-// the running k-th best cannot enter the top k, so its exact fp64 inputs are never fetched.
-// blend_scale = 1 for a shared topic vector (the record holds sqd itself) or sum |p_t| for a
-// per-query vector (the record holds max_t |PR[doc][t]|).  NaN/Inf fall through to the exact path.
-__device__ __forceinline__ bool screened_out(const Smem& s, float tr, float br, const float4& m32, float qf_inv,
-                                             float blend_scale) {
-  const float a = 0.33f * m32.z * blend_scale;
-  const float b = tr != 0.0f ? 0.38f * (tr * m32.x * qf_inv) : 0.0f;
-  const float c = br != 0.0f ? 0.29f * (br * m32.y * qf_inv) : 0.0f;
-  const float approx = (a + b + c) * 100.0f;
-  const float slack = (fabsf(a) + fabsf(b) + fabsf(c)) * 1e-2f + 1e-30f;  // 1e-4 relative, x100
-  return approx + slack < s.thr_f;  // false for NaN: those go to the exact path
-}
-// exact final rank from the fp64 sums (get_metadata.go:53-69) and the candidate test
-__device__ __forceinline__ void finish_exact(const ScoreParams& p, Smem& s, uint32_t q, uint64_t doc, double tr,
-                                             double br, double qm, uint32_t k) {
-  const DocMeta m = load_meta(p, q, doc);
-  // get_metadata.go:57-66.  x/y with x == 0 is 0 or NaN, and NaN becomes 0: skip the divide
-  double body = 0.0, title = 0.0;
-  if (br != 0.0) {
-    body = __ddiv_rn(br, __dmul_rn(m.mag_b, qm));
-    if (isnan(body)) body = 0.0;
-  }
-  if (tr != 0.0) {
-    title = __ddiv_rn(tr, __dmul_rn(m.mag_t, qm));
-    if (isnan(title)) title = 0.0;
-  }
-  // (0.33*sqd + 0.38*Title + 0.29*Body) * 100.0, left to right, no fusing (:69)
-  const double fin =
-      __dmul_rn(__dadd_rn(__dadd_rn(__dmul_rn(0.33, m.sqd), __dmul_rn(0.38, title)), __dmul_rn(0.29, body)), 100.0);
-  const unsigned long long key = score_key(fin);
-  if (key < s.gkey) return;  // below another slab's k-th best: cannot be in the query's top k
-  if (s.top_n < k || beats(key, (uint32_t)doc, s.thr_key, s.thr_doc)) {
-    const uint32_t j = atomicAdd(&s.n_cand, 1u);
-    s.cand_key[j] = key;
-    s.cand_doc[j] = (uint32_t)doc;
-  }
-}
-__device__ __forceinline__ void finish_doc(const ScoreParams& p, Smem& s, uint32_t q, uint64_t doc, double tr,
-                                           double br, const float4& m32, float qf_inv, float blend_scale,
-                                           double qm, uint32_t k) {
-  if (screened_out(s, (float)tr, (float)br, m32, qf_inv, blend_scale)) return;
-  finish_exact(p, s, q, doc, tr, br, qm, k);
-}
-
-// One list's postings of the sub-range into the accumulators; a list holds a doc at
-// most once, so plain read-modify-write is race free.  Four postings per thread are
-// fetched before the first is applied.
-__device__ __forceinline__ void accumulate_list(const TableView& tv, Smem& s, int tb, unsigned long long x0,
-                                                unsigned long long x1, uint64_t d0) {
-  constexpr int U = 4;
-  for (unsigned long long x = x0 + threadIdx.x; x < x1; x += (unsigned long long)U * kT) {
-    uint32_t d[U];
-    float w[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const unsigned long long xx = x + (unsigned long long)u * kT;
-      const bool ok = xx < x1;
-      d[u] = ok ? tv.doc_ids[xx] : 0xFFFFFFFFu;
-      w[u] = ok ? tv.w[xx] : 0.0f;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (d[u] == 0xFFFFFFFFu) continue;
-      const uint32_t slot = (uint32_t)(d[u] - d0);
-      s.acc[tb][slot] = __dadd_rn(s.acc[tb][slot], (double)w[u]);
-      mark_matched(s, slot);
-    }
-  }
-}
-
-// Sparse (query, slab) pairs: all postings of the slab fit in shared memory.  They are
-// tagged (doc offset, list sequence, weight), sorted, and every doc's run is folded in
-// sequence order -- the same sums as the dense path without touching empty sub-ranges.
-__device__ void sort_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t slab_lo, uint32_t n_kw, uint32_t n_ph,
-                          double qm, float qf_inv, float blend_scale, uint32_t k, unsigned long long& n_postings,
-                          unsigned long long& n_matched) {
-  unsigned long long* ent = reinterpret_cast<unsigned long long*>(&s.acc[0][0]);
-  const uint32_t tid = threadIdx.x, n_kw_lists = 2 * n_kw;
-  if (tid == 0) {
-    uint32_t run = 0;
-    for (uint32_t l = 0; l < n_kw_lists; ++l) {
-      s.bounds[l] = run;
-      run += s.len[l];
-    }
-    s.bounds[n_kw_lists] = run;
-    s.n_ent = run;
-  }
-  for (uint32_t l = n_kw_lists + tid; l < n_kw_lists + 2 * n_ph; l += kT) {  // phrase lists: whole slab range
-    s.cur[l] = s.base[l];
-    s.hi[l] = s.base[l] + s.len[l];
-  }
-  __syncthreads();
-  const uint32_t total_kw = s.bounds[n_kw_lists];
-  for (uint32_t idx = tid; idx < total_kw; idx += kT) {
-    uint32_t lo = 0, hi = n_kw_lists;  // last l with bounds[l] <= idx
-    while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (s.bounds[mid] <= idx) lo = mid; else hi = mid;
-    }
-    const TableView& tv = p.tab[lo & 1];
-    const unsigned long long at = s.base[lo] + (idx - s.bounds[lo]);
-    ent[idx] = make_entry((uint32_t)(tv.doc_ids[at] - slab_lo), lo, tv.w[at]);
-  }
-  if (tid == 0) n_postings += total_kw;
-  if (n_ph) {
-    apply_phrase<1>(p, s, 1, n_kw_lists, n_ph, slab_lo, n_kw_lists + 1, n_postings);
-    apply_phrase<1>(p, s, 0, n_kw_lists, n_ph, slab_lo, n_kw_lists, n_postings);
-  }
-  __syncthreads();
-  const uint32_t n = s.n_ent;
-  uint32_t n2 = 2;
-  while (n2 < n) n2 <<= 1;
-  for (uint32_t i = n + tid; i < n2; i += kT) ent[i] = ~0ull;
-  __syncthreads();
-  for (uint32_t kk = 2; kk <= n2; kk <<= 1) {
-    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
-      for (uint32_t i = tid; i < n2; i += kT) {
-        const uint32_t x = i ^ j;
-        if (x > i) {
-          const unsigned long long a = ent[i], b = ent[x];
-          if ((a > b) == ((i & kk) == 0)) {
-            ent[i] = b;
-            ent[x] = a;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-  for (uint32_t r0 = 0; r0 < n; r0 += kCand) {
-    const uint32_t r1 = min(n, r0 + kCand);
-    for (uint32_t i = r0 + tid; i < r1; i += kT) {
-      const unsigned long long e0 = ent[i];
-      const uint32_t off = (uint32_t)(e0 >> 40);
-      if (i > 0 && (uint32_t)(ent[i - 1] >> 40) == off) continue;  // not the head of a doc's run
-      double tr = 0.0, br = 0.0;
-      for (uint32_t j = i; j < n; ++j) {
-        const unsigned long long e = ent[j];
-        if ((uint32_t)(e >> 40) != off) break;
-        const double w = (double)__uint_as_float((uint32_t)e);
-        if ((e >> 32) & 1ull) br = __dadd_rn(br, w); else tr = __dadd_rn(tr, w);
-      }
-      ++n_matched;
-      finish_doc(p, s, q, slab_lo + off, tr, br, p.meta32[slab_lo + off], qf_inv, blend_scale, qm, k);
-    }
-    __syncthreads();
-    if (s.n_cand) merge_candidates(s, k);
-  }
-}
-
-// Sparse (query, slab) pairs without a phrase: the keyword lists are staged in shared memory as
-// they are -- every list is already sorted by doc -- and each posting looks its doc up in the
-// other lists by binary search.  The posting of the FIRST list that holds the doc owns it: it
-// folds the doc's weights in list (= query-token) order, which is the order of the reference's
-// sums, and finishes the doc.  No sort, no barriers inside the loop: the bitonic sort this
-// replaces cost ~100 ps per posting against ~10 ps in the dense path (78 block barriers per
-// 4096 entries), and 44 % of the benchmark's query tokens take this path.
-__device__ void owner_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t slab_lo, uint32_t n_kw, uint32_t n_ph,
-                           double qm, float qf_inv, float blend_scale, uint32_t k, unsigned long long& n_postings,
-                           unsigned long long& n_matched) {
-  uint32_t* soff = reinterpret_cast<uint32_t*>(&s.acc[0][0]);  // [kSortMax] doc offset in the slab
-  float* sw = reinterpret_cast<float*>(&s.acc[1][0]);          // [kSortMax] weight
-  const uint32_t tid = threadIdx.x, n_kw_lists = 2 * n_kw;
-  // With a phrase, its hits form two more "lists" behind the keyword lists: title hits (even index, so
-  // their weight joins TitleRank) then body hits (odd), each weight appended after the keyword weights as
-  // in main_retrieve.go:73-78.  They fit: a table's hits are at most its shortest phrase list, which is
-  // what `work` counted.
-  const uint32_t n_lists = n_kw_lists + (n_ph ? 2u : 0u);
-  if (tid == 0) {
-    uint32_t run = 0;
-    for (uint32_t l = 0; l < n_kw_lists; ++l) {
-      s.bounds[l] = run;
-      run += s.len[l];
-    }
-    s.bounds[n_kw_lists] = run;
-    s.n_ent = 0;
-  }
-  for (uint32_t l = n_kw_lists + tid; l < n_kw_lists + 2 * n_ph; l += kT) {  // phrase lists: whole range
-    s.cur[l] = s.base[l];
-    s.hi[l] = s.base[l] + s.len[l];
-  }
-  __syncthreads();
-  const uint32_t kw_total = s.bounds[n_kw_lists];
-  // stage: list by list, coalesced
-  for (uint32_t l = 0; l < n_kw_lists; ++l) {
-    const uint32_t len = s.len[l];
-    if (!len) continue;
-    const TableView& tv = p.tab[l & 1];
-    const unsigned long long at = s.base[l];
-    const uint32_t o = s.bounds[l];
-    for (uint32_t i = tid; i < len; i += kT) {
-      soff[o + i] = (uint32_t)(tv.doc_ids[at + i] - slab_lo);
-      sw[o + i] = tv.w[at + i];
-    }
-  }
-  if (tid == 0) n_postings += kw_total;
-  if (n_ph) {
-    // phrase hits of the title table, then of the body table, each sorted by doc (ranking by counting:
-    // a table holds a doc once, so the ranks are a permutation)
-    for (int tb = 0; tb < 2; ++tb) {
-      const uint32_t start = tb == 0 ? kw_total : s.bounds[n_kw_lists + 1];
-      apply_phrase<2>(p, s, tb, n_kw_lists, n_ph, slab_lo, start, n_postings);
-      __syncthreads();
-      const uint32_t cnt = s.n_ent;
-      uint32_t my_off[kSortMax / kT], my_rank[kSortMax / kT];
-      float my_w[kSortMax / kT];
-#pragma unroll 1
-      for (uint32_t c = 0, i = tid; i < cnt; i += kT, ++c) {
-        my_off[c] = soff[start + i];
-        my_w[c] = sw[start + i];
-        uint32_t r = 0;
-        for (uint32_t j = 0; j < cnt; ++j) r += soff[start + j] < my_off[c] ? 1u : 0u;
-        my_rank[c] = r;
-      }
-      __syncthreads();
-#pragma unroll 1
-      for (uint32_t c = 0, i = tid; i < cnt; i += kT, ++c) {
-        soff[start + my_rank[c]] = my_off[c];
-        sw[start + my_rank[c]] = my_w[c];
-      }
-      if (tid == 0) {
-        s.bounds[n_kw_lists + tb + 1] = start + cnt;
-        s.n_ent = 0;
-      }
-      __syncthreads();
-    }
-  } else {
-    __syncthreads();
-  }
-  const uint32_t total = s.bounds[n_lists];
-  // position of doc offset `off` in list j, or kNoDoc
-  auto find = [&](uint32_t j, uint32_t off) -> uint32_t {
-    uint32_t lo = s.bounds[j], hi = s.bounds[j + 1];
-    const uint32_t end = hi;
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (soff[mid] < off) lo = mid + 1; else hi = mid;
-    }
-    return (lo < end && soff[lo] == off) ? lo : kNoDoc;
-  };
-  for (uint32_t r0 = 0; r0 < total; r0 += kCand) {
-    const uint32_t r1 = min(total, r0 + kCand);
-    for (uint32_t idx = r0 + tid; idx < r1; idx += kT) {
-      uint32_t lo = 0, hi = n_lists;  // last l with bounds[l] <= idx
-      while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (s.bounds[mid] <= idx) lo = mid; else hi = mid;
-      }
-      const uint32_t l = lo, off = soff[idx];
-      bool owner = true;
-      for (uint32_t j = 0; j < l && owner; ++j) owner = find(j, off) == kNoDoc;
-      if (!owner) continue;
-      double tr = 0.0, br = 0.0;
-      {
-        const double w = (double)sw[idx];
-        if (l & 1u) br = w; else tr = w;
-      }
-      for (uint32_t j = l + 1; j < n_lists; ++j) {
-        const uint32_t at = find(j, off);
-        if (at == kNoDoc) continue;
-        const double w = (double)sw[at];
-        if (j & 1u) br = __dadd_rn(br, w); else tr = __dadd_rn(tr, w);
-      }
-      ++n_matched;
-      finish_doc(p, s, q, slab_lo + off, tr, br, p.meta32[slab_lo + off], qf_inv, blend_scale, qm, k);
-    }
-    __syncthreads();
-    if (s.n_cand) merge_candidates(s, k);
-  }
-}
-
-// ---- impact-vector path ----------------------------------------------------------------------
-// Keyword queries that contain one of the densest terms (>= 1/32 of the docs; 96 % of the
-// benchmark's postings belong to ~220 such terms).  Walking a 5M-posting list costs 8 B and ~150
-// thread instructions per posting in the accumulator path; here the term's whole contribution to
-// the SCREENING bound of a doc is one precomputed fp16 value (2 B, coalesced, no doc ids, no
-// atomics): U_t[d] >= 100 * (0.38 w_title/|title| + 0.29 w_body/|body|), rounded up, 0 = no
-// posting.  A sub-range of kDenseRange docs is streamed: bound(d) = blend_scale * Z[d] +
-// (sum of the dense tokens' U[d] + the sparse tokens' scattered fp32 impacts) / |q|, all terms
-// non-negative and rounded up, so bound(d) >= FinalRank(d).  Only docs whose bound reaches the
-// running threshold are evaluated exactly: their weights are looked up in the posting lists by
-// binary search and folded in query-token order -- the same fp64 sums, cosine and blend as the
-// other paths, so the top k is identical (tests/test_scoring_gpu.py compares the paths).
-__device__ __forceinline__ float half_bits_to_float(uint32_t h) {
-  return __half2float(__ushort_as_half((unsigned short)h));
-}
-
-// The doc's weight in list l of the query (slab range), if it has one: interpolation start (docs are
-// spread over the slab), gallop to bracket the doc, bisect.
-__device__ __forceinline__ bool find_index_in_list(const ScoreParams& p, const Smem& s, uint32_t l, uint32_t doc,
-                                                   uint64_t slab_lo, uint64_t slab_docs, unsigned long long& at) {
-  const uint32_t len = s.len[l];
-  if (!len) return false;
-  const uint32_t* __restrict__ docs = p.tab[l & 1].doc_ids + s.base[l];
-  uint32_t pos = (uint32_t)min((uint64_t)len - 1, (uint64_t)len * (doc - slab_lo) / slab_docs);
-  uint32_t lo, hi;  // invariant: docs[lo - 1] < doc (or lo == 0), docs[hi] >= doc (or hi == len)
-  if (docs[pos] < doc) {
-    lo = pos + 1;
-    uint32_t step = 16;
-    while (true) {
-      hi = min(len, lo + step);
-      if (hi == len || docs[hi] >= doc) break;
-      lo = hi + 1;
-      step <<= 1;
-    }
-  } else {
-    hi = pos;
-    uint32_t step = 16;
-    while (true) {
-      lo = hi > step ? hi - step : 0u;
-      if (lo == 0 || docs[lo - 1] < doc) break;
-      hi = lo - 1;
-      step <<= 1;
-    }
-  }
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (docs[mid] < doc) lo = mid + 1; else hi = mid;
-  }
-  if (lo == len || docs[lo] != doc) return false;
-  at = s.base[l] + lo;
-  return true;
-}
-__device__ __forceinline__ bool find_in_list(const ScoreParams& p, const Smem& s, uint32_t l, uint32_t doc,
-                                             uint64_t slab_lo, uint64_t slab_docs, float& w_out) {
-  unsigned long long at;
-  if (!find_index_in_list(p, s, l, doc, slab_lo, slab_docs, at)) return false;
-  w_out = p.tab[l & 1].w[at];
-  return true;
-}
-
-// phrase.go:53-109 for ONE doc and one table (the per-doc form of apply_phrase): lists l0+2*i+tb hold
-// token i.  The doc gets one weight = fp32 sum of the tokens' weights in phrase order iff every token has
-// a posting of the doc in this table and some position a of token 0 has a + i among token i's positions
-// (compared as (pos_i - float32(i)) == pos_0, phrase.go:144-146, util.go:185).
-__device__ bool phrase_hit(const ScoreParams& p, const Smem& s, int tb, uint32_t l0, uint32_t L, uint32_t doc,
-                           uint64_t slab_lo, uint64_t slab_docs, float& sum_out) {
-  const TableView& tv = p.tab[tb];
-  if (!tv.pos_ptr) return false;
-  unsigned long long pi[kMaxPh];
-  for (uint32_t i = 0; i < L; ++i)
-    if (!find_index_in_list(p, s, l0 + 2 * i + tb, doc, slab_lo, slab_docs, pi[i])) return false;
-  bool hit = false;
-  const unsigned long long a0 = tv.pos_ptr[pi[0]], a1 = tv.pos_ptr[pi[0] + 1];
-  for (unsigned long long x = a0; x < a1 && !hit; ++x) {
-    const float a = __fadd_rn(tv.pos[x], -0.0f);
-    bool ok = true;
-    for (uint32_t i = 1; i < L && ok; ++i) {
-      const float shift = (float)(uint8_t)i;
-      bool found = false;
-      for (unsigned long long y = tv.pos_ptr[pi[i]]; y < tv.pos_ptr[pi[i] + 1] && !found; ++y)
-        found = __fadd_rn(tv.pos[y], -shift) == a;
-      ok = found;
-    }
-    hit = ok;
-  }
-  if (!hit) return false;
-  float sum = 0.0f;  // phrase.go:59,69,83: float32 running sum in token order
-  for (uint32_t i = 0; i < L; ++i) sum = __fadd_rn(sum, tv.w[pi[i]]);
-  sum_out = sum;
-  return true;
-}
-
-// Exact evaluation of n survivors (slab offsets in the ring from position r0): four lanes per doc look it
-// up in four lists at a time, the weights are folded in list (= query-token) order -- the same fp64 sums
-// as the accumulator paths -- and the group's first lane finishes the doc.  Every thread of the CTA calls.
-__device__ __forceinline__ void evaluate_survivors(const ScoreParams& p, Smem& s, uint32_t q, const uint16_t* surv,
-                                                   uint32_t ring_mask, uint32_t r0, uint32_t n, uint64_t rel_base,
-                                                   uint32_t n_kw, uint32_t n_ph, uint64_t slab_lo, uint64_t slab_docs,
-                                                   double qm, uint32_t k) {
-  const uint32_t n_lists = 2 * n_kw;  // keyword lists; the phrase is evaluated after them
-  const uint32_t sub = threadIdx.x >> 2, gl = threadIdx.x & 3;
-  for (uint32_t base = 0; base < n; base += kT / 4) {
-    const uint32_t i = base + sub;
-    const bool active = i < n;
-    const uint32_t doc = active ? (uint32_t)(rel_base + surv[(r0 + i) & ring_mask]) : 0u;
-    double tr = 0.0, br = 0.0;
-    bool first_t = true, first_b = true;
-    for (uint32_t l0 = 0; l0 < n_lists; l0 += 4) {
-      const uint32_t l = l0 + gl;
-      float w = 0.0f;
-      const bool found = active && l < n_lists && find_in_list(p, s, l, doc, slab_lo, slab_docs, w);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool fj = __shfl_sync(0xFFFFFFFFu, found ? 1 : 0, j, 4) != 0;
-        const double wj = (double)__shfl_sync(0xFFFFFFFFu, w, j, 4);
-        if (!fj) continue;
-        if ((l0 + j) & 1u) {
-          br = first_b ? wj : __dadd_rn(br, wj);
-          first_b = false;
-        } else {
-          tr = first_t ? wj : __dadd_rn(tr, wj);
-          first_t = false;
-        }
-      }
-    }
-    if (active && gl == 0) {
-      bool matched = !(first_t && first_b);  // a keyword posting
-      if (n_ph) {  // the phrase's weight is appended after the keyword weights (main_retrieve.go:73-78)
-        float ws = 0.0f;
-        if (phrase_hit(p, s, 1, 2 * n_kw, n_ph, doc, slab_lo, slab_docs, ws)) {
-          br = first_b ? (double)ws : __dadd_rn(br, (double)ws);
-          matched = true;
-        }
-        if (phrase_hit(p, s, 0, 2 * n_kw, n_ph, doc, slab_lo, slab_docs, ws)) {
-          tr = first_t ? (double)ws : __dadd_rn(tr, (double)ws);
-          matched = true;
-        }
-      }
-      if (matched) finish_exact(p, s, q, doc, tr, br, qm, k);
-    }
-  }
-}
-
-// Whole-slab stream of the impact-vector path for keyword queries whose tokens in this slab are all
-// dense (no scattered sparse impacts) once a threshold exists: no barriers inside, two 8-doc groups
-// per thread and step with all loads issued first.  Survivors go to the ring as 16-bit slab offsets;
-// returns false (uniformly, after a barrier) if the ring overflowed -- the caller then redoes the slab
-// sub-range by sub-range.  ND = number of dense tokens when it is 1 or 2 (vector bases in registers),
-// 0 = any.
-template <int ND>
-__device__ __forceinline__ bool dtiv_stream_slab(const ScoreParams& p, Smem& s, uint16_t* surv, uint32_t ring_mask,
-                                                 uint32_t surv_done, uint64_t slab_lo, uint64_t slab_hi, uint32_t nd,
-                                                 float za, float blend_scale, float qf_inv, float thr_f,
-                                                 const uint32_t* excl, uint32_t& my_matched) {
-  // excl: bitmap over the slab of docs that also have a sparse-token posting; those are scored by the
-  // caller (their bound needs the sparse impacts), so they are masked out here.  NULL = none.
-  const uint32_t tid = threadIdx.x;
-  const uint32_t n_docs = (uint32_t)(slab_hi - slab_lo);
-  const uint16_t* __restrict__ base[ND ? ND : 1];
-#pragma unroll
-  for (int i = 0; i < (ND ? ND : 1); ++i) base[i] = p.uvec + (size_t)s.dense_slots[i] * p.d_pad + slab_lo;
-  const uint16_t* __restrict__ zv = p.zvec + slab_lo;
-  bool ovf = false;
-  auto process = [&](const float (&sum)[8], uint32_t off) {
-    uint32_t present = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) present |= (sum[j] > 0.0f ? 1u : 0u) << j;  // impacts are >= 0, > 0 for a posting
-    if (excl) present &= ~((excl[off >> 5] >> (off & 31)) & 0xFFu);
-    if (off + 8 > n_docs) present &= (1u << (n_docs - off)) - 1u;
-    if (!present) return;
-    my_matched += __popc(present);
-    const float gmax = fmaxf(fmaxf(fmaxf(sum[0], sum[1]), fmaxf(sum[2], sum[3])),
-                             fmaxf(fmaxf(sum[4], sum[5]), fmaxf(sum[6], sum[7])));
-    {
-      const float b = qf_inv * gmax;
-      if ((za + b) + (fabsf(za) + fabsf(b)) * 1e-4f + 1e-30f < thr_f) return;
-    }
-    const uint4 zz = __ldg(reinterpret_cast<const uint4*>(zv + off));
-    const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (!((present >> j) & 1u)) continue;
-      const float z = half_bits_to_float(j & 1 ? zw[j >> 1] >> 16 : zw[j >> 1] & 0xFFFFu);
-      const float a = blend_scale * z, b = qf_inv * sum[j];
-      if ((a + b) + (fabsf(a) + fabsf(b)) * 1e-4f + 1e-30f < thr_f) continue;  // NaN and +inf stay in
-      const uint32_t pos = atomicAdd(&s.n_list, 1u);
-      if (pos - surv_done > ring_mask) ovf = true; else surv[pos & ring_mask] = (uint16_t)(off + j);
-    }
-  };
-  auto add8 = [](float (&sum)[8], const uint4& u) {
-    const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&uw[j]));
-      sum[2 * j] += f.x;
-      sum[2 * j + 1] += f.y;
-    }
-  };
-#pragma unroll 1
-  for (uint32_t off = 8 * tid; off < n_docs; off += 16 * kT) {
-    const uint32_t off2 = off + 8 * kT;
-    const bool has2 = off2 < n_docs;
-    float sa[8], sb[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sa[j] = sb[j] = 0.0f;
-    if (ND) {
-      uint4 ua[ND ? ND : 1], ub[ND ? ND : 1];
-#pragma unroll
-      for (int i = 0; i < (ND ? ND : 1); ++i) {
-        ua[i] = __ldg(reinterpret_cast<const uint4*>(base[i] + off));
-        ub[i] = has2 ? __ldg(reinterpret_cast<const uint4*>(base[i] + off2)) : make_uint4(0u, 0u, 0u, 0u);
-      }
-#pragma unroll
-      for (int i = 0; i < (ND ? ND : 1); ++i) {
-        add8(sa, ua[i]);
-        add8(sb, ub[i]);
-      }
-    } else {
-      for (uint32_t i = 0; i < nd; ++i) {
-        const uint16_t* b = p.uvec + (size_t)s.dense_slots[i] * p.d_pad + slab_lo;
-        const uint4 ua = __ldg(reinterpret_cast<const uint4*>(b + off));
-        const uint4 ub = has2 ? __ldg(reinterpret_cast<const uint4*>(b + off2)) : make_uint4(0u, 0u, 0u, 0u);
-        add8(sa, ua);
-        add8(sb, ub);
-      }
-    }
-    process(sa, off);
-    if (has2) process(sb, off2);
-  }
-  return !__syncthreads_or(ovf ? 1 : 0);
-}
-
-__device__ void dtiv_path(const ScoreParams& p, Smem& s, uint32_t q, uint64_t slab_lo, uint64_t slab_hi, uint32_t n_kw,
-                          uint32_t n_ph, double qm, float qf_inv, float blend_scale, uint32_t k,
-                          unsigned long long& n_postings, unsigned long long& n_matched) {
-  // Phrase tokens take part in the bound like keyword tokens: the phrase adds at most the sum of its
-  // tokens' weights per table (phrase.go:97-106), and only if the positions line up, which the exact
-  // evaluation of the survivors decides.  "Present" then means "has a posting of some query token".
-  constexpr int RD = kDenseRange;
-  constexpr uint32_t kRing = 2 * RD;                               // survivor ring capacity
-  float* sacc = reinterpret_cast<float*>(&s.acc[0][0]);            // [RD] sparse tokens' impact sums
-  uint16_t* surv = reinterpret_cast<uint16_t*>(&s.acc[1][0]);      // [kRing] slab-relative slots >> 0 of survivors
-  uint32_t* dbits = s.dbits;                                       // [RD / 32] presence from sparse tokens
-  const uint32_t tid = threadIdx.x, n_lists = 2 * (n_kw + n_ph);
-  const uint32_t nd = s.n_dense_tok, nsp = s.n_sparse_tok;
-  const uint32_t n_sub = (uint32_t)((slab_hi - slab_lo + RD - 1) / RD);
-  if (tid == 0) {
-    unsigned long long tot = 0;
-    for (uint32_t l = 0; l < n_lists; ++l) tot += s.len[l];
-    n_postings += tot;  // nominal: the posting lists this (query, slab) pair covers
-  }
-  // sparse tokens: posting offsets at every sub-range boundary
-  bool has_sparse = false;
-  for (uint32_t i = 0; i < nsp; ++i) has_sparse |= (s.len[2 * s.sparse_toks[i]] | s.len[2 * s.sparse_toks[i] + 1]) != 0;
-  // whole-slab mode (below) applies when the sparse tokens have few postings here and a threshold exists
-  constexpr uint32_t kSparseStage = 2048;
-  const bool flush_each = (slab_hi - slab_lo) > 65536u;
-  uint32_t sp_total = 0;
-  if (has_sparse)
-    for (uint32_t i = 0; i < nsp; ++i) sp_total += s.len[2 * s.sparse_toks[i]] + s.len[2 * s.sparse_toks[i] + 1];
-  const bool whole_slab = !flush_each && sp_total <= kSparseStage && s.thr_f != -__int_as_float(0x7f800000);
-  auto setup_subranges = [&]() {  // sub-range mode: boundary table of the sparse lists, clean scratch
-    for (uint32_t idx = tid; idx < 2 * nsp * (n_sub + 1); idx += kT) {
-      const uint32_t li = idx / (n_sub + 1), j = idx % (n_sub + 1);
-      const uint32_t l = 2 * s.sparse_toks[li >> 1] + (li & 1);
-      const uint64_t target = min(slab_hi, slab_lo + (uint64_t)j * RD);
-      s.bounds[idx] = s.len[l] ? (uint32_t)(lower_bound_doc(p.tab[l & 1].doc_ids, s.base[l], s.base[l] + s.len[l], target) - s.base[l]) : 0u;
-    }
-    for (uint32_t i = tid; i < RD; i += kT) sacc[i] = 0.0f;
-    for (uint32_t i = tid; i < RD / 32; i += kT) dbits[i] = 0;
-  };
-  if (has_sparse && !whole_slab) setup_subranges();
-  // largest blend term of the slab (group-level rejection test): one zblk entry per thread, warp max,
-  // combined through shared memory; a NaN entry disables the rejection
-  {
-    const uint64_t b0 = slab_lo / kRange, nb = (slab_hi - slab_lo + kRange - 1) / kRange;
-    float zm = -__int_as_float(0x7f800000);
-    bool nan = false;
-    for (uint64_t b = tid; b < nb; b += kT) {
-      const float z = p.zblk[b0 + b];
-      nan |= z != z;
-      zm = fmaxf(zm, z);
-    }
-    for (int o = 16; o; o >>= 1) zm = fmaxf(zm, __shfl_xor_sync(0xFFFFFFFFu, zm, o));
-    nan = __any_sync(0xFFFFFFFFu, nan);
-    if ((tid & 31) == 0) s.zred[tid >> 5] = nan ? __int_as_float(0x7fc00000) : zm;
-  }
-  __syncthreads();
-  float za;
-  {
-    float zm = s.zred[0];
-    bool nan = zm != zm;
-    for (int w = 1; w < kT / 32; ++w) {
-      const float z = s.zred[w];
-      nan |= z != z;
-      zm = fmaxf(zm, z);
-    }
-    za = nan ? __int_as_float(0x7fc00000) : blend_scale * zm;
-  }
-  // survivors carry (sub-range, slot) as a slab-relative doc offset in 16 bits when the slab allows it,
-  // else they are flushed every sub-range (flush_each)
-  uint32_t surv_done = s.n_list;
-  uint32_t my_matched = 0;
-  // Whole-slab mode: every token of the slab is dense, or the sparse tokens have few postings here.
-  if (whole_slab) {
-    const float thr_f = s.thr_f;
-    // mixed layout: acc[0] = staged sparse postings (slab offset, impact), acc[1] = survivor ring (4096) + bitmap
-    uint32_t* soff = reinterpret_cast<uint32_t*>(&s.acc[0][0]);
-    float* simp = reinterpret_cast<float*>(soff + kSparseStage);
-    uint32_t* excl = reinterpret_cast<uint32_t*>(surv + RD);  // [65536 / 32] words = 8 KB
-    const uint32_t ring_mask = has_sparse ? (uint32_t)RD - 1u : kRing - 1u;
-    if (has_sparse) {
-      __syncthreads();  // the sparse scratch set up above (sacc / bounds) is not used in this mode
-      for (uint32_t i = tid; i < 65536 / 32; i += kT) excl[i] = 0;
-      if (tid == 0) {
-        uint32_t run = 0;
-        for (uint32_t li = 0; li < 2 * nsp; ++li) {
-          s.bounds[li] = run;
-          run += s.len[2 * s.sparse_toks[li >> 1] + (li & 1)];
-        }
-        s.bounds[2 * nsp] = run;
-      }
-      __syncthreads();
-      for (uint32_t li = 0; li < 2 * nsp; ++li) {
-        const uint32_t l = 2 * s.sparse_toks[li >> 1] + (li & 1), len = s.len[l];
-        const TableView& tv = p.tab[l & 1];
-        for (uint32_t i = tid; i < len; i += kT) {
-          const uint32_t doc = tv.doc_ids[s.base[l] + i];
-          const float w = tv.w[s.base[l] + i];
-          const float4 m = p.meta32[doc];
-          float v = (l & 1) ? 29.0f * (w * m.y) : 38.0f * (w * m.x);
-          v = fmaxf(v, 0.0f) * 1.00001f;
-          const uint32_t off = (uint32_t)(doc - slab_lo);
-          soff[s.bounds[li] + i] = off;
-          simp[s.bounds[li] + i] = v;
-          atomicOr(&excl[off >> 5], 1u << (off & 31));
-        }
-      }
-      __syncthreads();
-    }
-    uint32_t cnt = 0;
-    bool ovf_forced = false;
-    if (has_sparse) {
-      // docs with a sparse posting: the first sparse list that holds the doc owns it and bounds it with the
-      // doc's sparse impacts plus its entries of the dense vectors
-      auto find = [&](uint32_t lj, uint32_t off) -> uint32_t {
-        uint32_t lo = s.bounds[lj], hi = s.bounds[lj + 1];
-        const uint32_t end = hi;
-        while (lo < hi) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (soff[mid] < off) lo = mid + 1; else hi = mid;
-        }
-        return (lo < end && soff[lo] == off) ? lo : kNoDoc;
-      };
-      for (uint32_t idx = tid; idx < sp_total; idx += kT) {
-        uint32_t lo = 0, hi = 2 * nsp;  // last li with bounds[li] <= idx
-        while (hi - lo > 1) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (s.bounds[mid] <= idx) lo = mid; else hi = mid;
-        }
-        const uint32_t li = lo, off = soff[idx];
-        bool owner = true;
-        for (uint32_t j = 0; j < li && owner; ++j) owner = find(j, off) == kNoDoc;
-        if (!owner) continue;
-        ++cnt;
-        float sum = simp[idx];
-        for (uint32_t j = li + 1; j < 2 * nsp; ++j) {
-          const uint32_t at = find(j, off);
-          if (at != kNoDoc) sum += simp[at];
-        }
-        for (uint32_t i = 0; i < nd; ++i)
-          sum += half_bits_to_float(p.uvec[(size_t)s.dense_slots[i] * p.d_pad + slab_lo + off]);
-        const float z = half_bits_to_float(p.zvec[slab_lo + off]);
-        const float a = blend_scale * z, b = qf_inv * sum;
-        if ((a + b) + (fabsf(a) + fabsf(b)) * 1e-4f + 1e-30f < thr_f) continue;
-        const uint32_t pos = atomicAdd(&s.n_list, 1u);
-        if (pos - surv_done > ring_mask) ovf_forced = true; else surv[pos & ring_mask] = (uint16_t)off;
-      }
-    }
-    const uint32_t* ex = has_sparse ? excl : nullptr;
-    bool ok;
-    if (nd == 1) ok = dtiv_stream_slab<1>(p, s, surv, ring_mask, surv_done, slab_lo, slab_hi, nd, za, blend_scale, qf_inv, thr_f, ex, cnt);
-    else if (nd == 2) ok = dtiv_stream_slab<2>(p, s, surv, ring_mask, surv_done, slab_lo, slab_hi, nd, za, blend_scale, qf_inv, thr_f, ex, cnt);
-    else ok = dtiv_stream_slab<0>(p, s, surv, ring_mask, surv_done, slab_lo, slab_hi, nd, za, blend_scale, qf_inv, thr_f, ex, cnt);
-    ok = !__syncthreads_or(ovf_forced ? 1 : 0) && ok;
-    if (ok) {
-      n_matched += cnt;
-      const uint32_t surv_end = s.n_list;
-      for (uint32_t r0 = surv_done; r0 != surv_end; r0 += min((uint32_t)kCand, surv_end - r0)) {
-        const uint32_t n_round = min((uint32_t)kCand, surv_end - r0);
-        evaluate_survivors(p, s, q, surv, ring_mask, r0, n_round, slab_lo, n_kw, n_ph, slab_lo, slab_hi - slab_lo, qm, k);
-        __syncthreads();
-        if (s.n_cand) merge_candidates(s, k);
-      }
-      return;
-    }
-    // the survivor ring overflowed (masses of ties at the threshold): forget the pass, go sub-range by sub-range
-    if (tid == 0) s.n_list = surv_done;
-    if (has_sparse) setup_subranges();  // the staged postings used the sub-range scratch
-    __syncthreads();
-  }
-  for (uint32_t sj = 0; sj < n_sub; ++sj) {
-    const uint64_t d0 = slab_lo + (uint64_t)sj * RD, d1 = min(slab_hi, d0 + RD);
-    const uint32_t rel0 = flush_each ? 0u : (uint32_t)(d0 - slab_lo);
-    bool any_sp = false;
-    if (has_sparse) {
-      for (uint32_t li = 0; li < 2 * nsp; ++li)
-        any_sp |= s.bounds[li * (n_sub + 1) + sj] != s.bounds[li * (n_sub + 1) + sj + 1];
-    }
-    if (any_sp) {
-      for (uint32_t li = 0; li < 2 * nsp; ++li) {
-        const uint32_t l = 2 * s.sparse_toks[li >> 1] + (li & 1);
-        const unsigned long long x0 = s.base[l] + s.bounds[li * (n_sub + 1) + sj];
-        const unsigned long long x1 = s.base[l] + s.bounds[li * (n_sub + 1) + sj + 1];
-        const TableView& tv = p.tab[l & 1];
-        for (unsigned long long x = x0 + tid; x < x1; x += kT) {
-          const uint32_t doc = tv.doc_ids[x];
-          const float w = tv.w[x];
-          const float4 m = p.meta32[doc];
-          float v = (l & 1) ? 29.0f * (w * m.y) : 38.0f * (w * m.x);
-          v = fmaxf(v, 0.0f) * 1.00001f;  // NaN -> 0: a NaN component counts as 0 in the reference too
-          const uint32_t slot = (uint32_t)(doc - d0);
-          atomicAdd(&sacc[slot], v);
-          atomicOr(&dbits[slot >> 5], 1u << (slot & 31));
-        }
-      }
-      __syncthreads();
-    }
-    // stream the sub-range: 8 consecutive docs per thread and step.  A group whose best bound (largest
-    // impact sum, the block's largest blend term) stays below the threshold is dropped with one test.
-    const float thr_f = s.thr_f;
-#pragma unroll 1
-    for (uint32_t g0 = 0; g0 < RD; g0 += 8 * kT) {
-      const uint32_t slot0 = g0 + 8 * tid;
-      const uint64_t doc0 = d0 + slot0;
-      if (doc0 >= d1) continue;
-      float sum[8];
-      uint32_t nzw[4] = {0u, 0u, 0u, 0u};  // 0xFFFF per half-word: some dense token has a posting of that doc
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sum[j] = 0.0f;
-      for (uint32_t i = 0; i < nd; ++i) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.uvec + (size_t)s.dense_slots[i] * p.d_pad + doc0));
-        const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&uw[j]));
-          sum[2 * j] += f.x;
-          sum[2 * j + 1] += f.y;
-          nzw[j] |= __vcmpne2(uw[j], 0u);
-        }
-      }
-      uint32_t sp_bits = 0;
-      if (any_sp) {
-        sp_bits = (dbits[slot0 >> 5] >> (slot0 & 31)) & 0xFFu;
-        const float4 a0 = *reinterpret_cast<const float4*>(sacc + slot0);
-        const float4 a1 = *reinterpret_cast<const float4*>(sacc + slot0 + 4);
-        sum[0] += a0.x; sum[1] += a0.y; sum[2] += a0.z; sum[3] += a0.w;
-        sum[4] += a1.x; sum[5] += a1.y; sum[6] += a1.z; sum[7] += a1.w;
-      }
-      // present docs (dense posting or sparse posting), docs past the slab end masked out
-      uint32_t present = sp_bits;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) present |= ((nzw[j] & 1u) << (2 * j)) | (((nzw[j] >> 16) & 1u) << (2 * j + 1));
-      if (doc0 + 8 > d1) present &= (1u << (uint32_t)(d1 - doc0)) - 1u;
-      my_matched += __popc(present);
-      if (!present) continue;
-      float gmax = fmaxf(fmaxf(fmaxf(sum[0], sum[1]), fmaxf(sum[2], sum[3])), fmaxf(fmaxf(sum[4], sum[5]), fmaxf(sum[6], sum[7])));
-      {
-        const float b = qf_inv * gmax;
-        // fmaxf drops NaNs: a NaN sum can only come from inf - inf, impossible here (all terms >= 0)
-        if ((za + b) + (fabsf(za) + fabsf(b)) * 1e-4f + 1e-30f < thr_f) continue;
-      }
-      const uint4 zz = __ldg(reinterpret_cast<const uint4*>(p.zvec + doc0));
-      const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (!((present >> j) & 1u)) continue;
-        const float z = half_bits_to_float(j & 1 ? zw[j >> 1] >> 16 : zw[j >> 1] & 0xFFFFu);
-        const float a = blend_scale * z, b = qf_inv * sum[j];
-        if ((a + b) + (fabsf(a) + fabsf(b)) * 1e-4f + 1e-30f < thr_f) continue;  // NaN and +inf stay in
-        surv[atomicAdd(&s.n_list, 1u) & (kRing - 1)] = (uint16_t)(rel0 + slot0 + j);
-      }
-    }
-    __syncthreads();
-    // clean the sparse scratch for the next sub-range (not read again before the next barrier)
-    if (any_sp) {
-      for (uint32_t i = tid; i < RD; i += kT) sacc[i] = 0.0f;
-      for (uint32_t i = tid; i < RD / 32; i += kT) dbits[i] = 0;
-    }
-    // Exact evaluation of the survivors stalls the block on a few threads' dependent lookups, so it
-    // is deferred until the slab ends, the ring could overflow, or no threshold exists yet.
-    const uint32_t surv_end = s.n_list;
-    const bool flush = flush_each || sj + 1 == n_sub || surv_end - surv_done > (uint32_t)RD ||
-                       (surv_end != surv_done && thr_f == -__int_as_float(0x7f800000));
-    if (flush) {
-      const uint64_t rel_base = flush_each ? d0 : slab_lo;
-      for (uint32_t r0 = surv_done; r0 != surv_end; r0 += min((uint32_t)kCand, surv_end - r0)) {
-        const uint32_t cnt = min((uint32_t)kCand, surv_end - r0);
-        evaluate_survivors(p, s, q, surv, kRing - 1, r0, cnt, rel_base, n_kw, n_ph, slab_lo, slab_hi - slab_lo, qm, k);
-        __syncthreads();
-        if (s.n_cand) merge_candidates(s, k);
-      }
-      surv_done = surv_end;
-    }
-    if (any_sp) __syncthreads();  // the scratch is clean before the next scatter
-  }
-  n_matched += my_matched;
-}
-
-// PHRASE = false: the batch has no phrase token; that instantiation carries none of the phrase code (the
-// keyword paths lose ~9 % to register pressure and code size otherwise).
-template <bool PHRASE>
-__global__ void __launch_bounds__(kT, 3) k_score(ScoreParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
-  const uint32_t q = blockIdx.x % p.n_q, slab = blockIdx.x / p.n_q;  // slab-major launch order
-  const uint32_t glen = p.group_len[(size_t)q * p.n_slabs + slab];
-  if (glen == 0) return;  // scored by the CTA that leads this slab's group (its part_count stays 0)
-  const uint32_t tid = threadIdx.x;
-  const uint64_t kb = p.kw_ptr[q], ke = p.kw_ptr[q + 1];
-  const uint64_t pb = (PHRASE && p.ph_ptr) ? p.ph_ptr[q] : 0, pe = (PHRASE && p.ph_ptr) ? p.ph_ptr[q + 1] : 0;
-  const uint32_t n_kw = (uint32_t)(ke - kb);
-  uint32_t n_ph = PHRASE ? (uint32_t)(pe - pb) : 0u;
-  const uint32_t q_len = n_kw + n_ph;            // main_retrieve.go:90
-  if (n_ph > kMaxPh) n_ph = 0;                   // host rejects 33..256; >256 can never match (uint8 TermPos)
-  const uint32_t n_tok = n_kw + n_ph, n_lists = 2 * n_tok;
-  const uint64_t slab_lo = (uint64_t)slab * p.slab_docs;
-  const uint64_t slab_hi = min(p.D, slab_lo + (uint64_t)glen * p.slab_docs);
-  const uint32_t k = p.k;
-
-  if (tid == 0) {
-    s.n_cand = 0;
-    s.n_ent = 0;
-    s.n_list = 0;
-    s.top_n = 0;
-    s.top_buf = 0;
-    s.thr_key = 0;
-    s.thr_doc = kNoDoc;
-    // Running bound of the query: CTAs are launched slab-major, so by the time slab j of a query
-    // starts, earlier slabs have usually published their k-th best score.  A doc scoring strictly
-    // below ANY slab's k-th best cannot be among the query's k best, so it is dropped here exactly
-    // as the per-slab threshold drops it; ties are kept (the doc id decides them in k_merge).  The
-    // result does not depend on which bound a CTA happens to see.
-    const unsigned long long g = p.use_qthr ? *reinterpret_cast<volatile unsigned long long*>(p.qthr + q) : 0ull;
-    const double gs = key_score(g);
-    s.gkey = g;
-    s.gthr_f = (g == 0ull || isnan(gs)) ? -__int_as_float(0x7f800000) : __double2float_rd(gs);
-    s.thr_f = s.gthr_f;
-  }
-  // which keyword tokens have an impact vector
-  if (tid == 0) {
-    uint32_t ndt = 0, nst = 0, ndk = 0;
-    for (uint32_t i = 0; i < n_tok; ++i) {
-      const uint32_t term = i < n_kw ? p.kw_terms[kb + i] : p.ph_terms[pb + (i - n_kw)];
-      const uint8_t slot = (p.uvec && term < p.dense_map_V) ? p.dense_map[term] : (uint8_t)255;
-      s.tok_dense[i] = slot;
-      if (slot != 255) s.dense_slots[ndt++] = slot; else s.sparse_toks[nst++] = (uint8_t)i;
-      if (slot != 255 && i < n_kw) ++ndk;
-    }
-    s.n_dense_kw = ndk;
-    s.n_dense_tok = ndt;
-    s.n_sparse_tok = nst;
-  }
-  // narrow every list to the slab
-  for (uint32_t l = tid; l < n_lists; l += kT) {
-    const uint32_t tok = l >> 1, tb = l & 1;
-    const uint32_t term = tok < n_kw ? p.kw_terms[kb + tok] : p.ph_terms[pb + (tok - n_kw)];
-    const TableView& tv = p.tab[tb];
-    unsigned long long a = 0;
-    if (tv.term_ptr && term < tv.V) a = tv.term_ptr[term];  // unknown term => empty row (main_retrieve.go:193,218)
-    // slab boundaries of every list were located once for the whole batch (k_narrow)
-    const uint32_t* nar = p.narrow + ((size_t)2 * (kb + pb) + l) * (p.n_slabs + 1) + slab;
-    const uint32_t o0 = nar[0], o1 = nar[glen];
-    s.base[l] = a + o0;
-    s.len[l] = o1 - o0;
-  }
-  __syncthreads();
-
-  // how much work is there in this slab?  (uniform: every thread reads the same shared values)
-  unsigned long long work = 0;
-  for (uint32_t l = 0; l < 2 * n_kw; ++l) work += s.len[l];
-  for (int tb = 0; tb < 2 && n_ph; ++tb) {
-    uint32_t mn = 0xFFFFFFFFu;
-    for (uint32_t i = 0; i < n_ph; ++i) mn = min(mn, s.len[2 * n_kw + 2 * i + tb]);
-    work += mn;  // a phrase can hit at most once per posting of its shortest list
-  }
-  const double qm = sqrt((double)q_len);  // get_metadata.go:53
-  const float qf_inv = 1.0f / (float)qm;
-  float blend_scale = 1.0f;  // screening: |sum_t p_t PR_t| <= (sum_t |p_t|) * max_t |PR_t|
-  if (p.probs) {
-    blend_scale = 0.0f;
-    for (uint32_t t = 0; t < p.T; ++t) blend_scale += fabsf((float)p.probs[(uint64_t)q * p.T + t]);
-    blend_scale *= 1.0001f;
-  }
-  // screening coefficients: 100 * (0.33 * blend, 0.38 / |q|, 0.29 / |q|)
-  const float sc_a = 33.0f * blend_scale, sc_t = 38.0f * qf_inv, sc_b = 29.0f * qf_inv;
-  unsigned long long n_postings = 0, n_matched = 0;
-
-  if (work == 0) {
-    // nothing of this query lives in this slab
-  } else if (work > p.sort_max &&
-             // a phrase query needs a dense KEYWORD token: its many matches set the threshold the phrase
-             // docs are screened against (phrase hits alone are too rare to ever establish one)
-             (n_ph ? (p.phrase_dense && s.n_dense_kw > 0) : s.n_dense_tok > 0) &&
-             2 * s.n_sparse_tok * ((slab_hi - slab_lo + kDenseRange - 1) / kDenseRange + 1) <= (uint64_t)kBounds) {
-    dtiv_path(p, s, q, slab_lo, slab_hi, n_kw, n_ph, qm, qf_inv, blend_scale, k, n_postings, n_matched);
-  } else if (work <= p.sort_max && p.owner_path && (n_ph == 0 || slab_hi - slab_lo <= 0xFFFFFFFFull)) {
-    owner_path(p, s, q, slab_lo, n_kw, n_ph, qm, qf_inv, blend_scale, k, n_postings, n_matched);
-  } else if (work <= p.sort_max && slab_hi - slab_lo <= (1ull << 24)) {
-    sort_path(p, s, q, slab_lo, n_kw, n_ph, qm, qf_inv, blend_scale, k, n_postings, n_matched);
-  } else {
-  for (uint32_t i = tid; i < kRange; i += kT) {
-    s.acc[0][i] = 0.0;
-    s.acc[1][i] = 0.0;
-  }
-  for (uint32_t i = tid; i < kRange / 32; i += kT) s.bits[i] = 0;
-  uint32_t list_done = 0;  // n_list at the end of the previous sub-range (uniform)
-  // Sub-range boundaries of every list are found up front, all threads searching
-  // in parallel (one dependent-load chain per CTA pass instead of one per sub-range).
-  const uint32_t n_sub = (uint32_t)((slab_hi - slab_lo + kRange - 1) / kRange);
-  const uint32_t pass_sub = n_lists ? max(1u, min(n_sub, (uint32_t)kBounds / n_lists - 1u)) : n_sub;
-  for (uint32_t sub0 = 0; sub0 < n_sub; sub0 += pass_sub) {
-  const uint32_t nb = min(pass_sub, n_sub - sub0);
-  __syncthreads();
-  for (uint32_t idx = tid; idx < n_lists * (nb + 1); idx += kT) {
-    const uint32_t l = idx / (nb + 1), j = idx % (nb + 1);
-    const uint64_t target = min(slab_hi, slab_lo + (uint64_t)(sub0 + j) * kRange);
-    const uint32_t* docs = p.tab[l & 1].doc_ids;
-    s.bounds[idx] = s.len[l] ? (uint32_t)(lower_bound_doc(docs, s.base[l], s.base[l] + s.len[l], target) - s.base[l]) : 0u;
-  }
-  __syncthreads();
-  for (uint32_t sj = 0; sj < nb; ++sj) {
-    const uint64_t d0 = slab_lo + (uint64_t)(sub0 + sj) * kRange;
-    // list l covers postings [base + bounds[l][sj], base + bounds[l][sj+1]) in this sub-range
-    auto lo_of = [&](uint32_t l) { return s.base[l] + s.bounds[l * (nb + 1) + sj]; };
-    auto hi_of = [&](uint32_t l) { return s.base[l] + s.bounds[l * (nb + 1) + sj + 1]; };
-
-    // the screening records of this sub-range (kRange x 16 B, one 128-byte line per thread) are
-    // requested now so that they arrive in L1 while the postings are being applied
-    if (p.prefetch_meta) {
-      const uint64_t first = d0 + (uint64_t)tid * 8;
-      if (first < p.D) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.meta32 + first));
-    }
-    // keyword tokens in query order (duplicates count again); a barrier only after a token
-    // that touched the accumulators
-    bool any = false;
-    for (uint32_t i = 0; i < n_kw; ++i) {
-      const unsigned long long t0 = lo_of(2 * i), t1 = hi_of(2 * i), b0 = lo_of(2 * i + 1), b1 = hi_of(2 * i + 1);
-      if (t1 == t0 && b1 == b0) continue;
-      if (any) __syncthreads();  // the previous token's updates are complete
-      any = true;
-      accumulate_list(p.tab[1], s, 1, b0, b1, d0);
-      accumulate_list(p.tab[0], s, 0, t0, t1, d0);
-      if (tid == 0) n_postings += (t1 - t0) + (b1 - b0);
-    }
-    // the phrase's weight is appended after the keyword weights (main_retrieve.go:73-78)
-    if (n_ph) {
-      bool ph_any = false;
-      for (uint32_t i = 0; i < 2 * n_ph; ++i) ph_any |= hi_of(2 * n_kw + i) != lo_of(2 * n_kw + i);
-      if (ph_any) {
-        if (any) __syncthreads();
-        for (uint32_t l = 2 * n_kw + tid; l < n_lists; l += kT) {
-          s.cur[l] = lo_of(l);
-          s.hi[l] = hi_of(l);
-        }
-        __syncthreads();
-        any = true;
-        apply_phrase<0>(p, s, 1, 2 * n_kw, n_ph, d0, 0, n_postings);
-        apply_phrase<0>(p, s, 0, 2 * n_kw, n_ph, d0, 0, n_postings);
-      }
-    }
-    if (!any) continue;  // uniform
-    __syncthreads();
-
-    // finish the matched docs from the first-touch list, kCand (the candidate buffer's capacity)
-    // per round; a thread's docs of a round are fetched together before any of them is scored.
-    // n_list only grows (ring index), so nothing but the bitmap needs a reset.
-    const uint32_t list_end = s.n_list;
-    if (tid == 0) n_matched += list_end - list_done;
-    if (tid < kRange / 32) s.bits[tid] = 0;  // not read again before the barrier below
-    const float4* meta_base = p.meta32 + d0;
-    constexpr int kPer = kCand / kT;
-    for (uint32_t r0 = list_done; r0 != list_end; r0 += min((uint32_t)kCand, list_end - r0)) {
-      bool has[kPer];
-      uint32_t slot[kPer];
-      float4 meta[kPer];
-      double tr[kPer], br[kPer];
-#pragma unroll
-      for (int c = 0; c < kPer; ++c) {
-        const uint32_t i = tid + c * kT;
-        has[c] = i < list_end - r0;
-        slot[c] = has[c] ? s.mlist[(r0 + i) & (kRange - 1)] : 0u;
-      }
-#pragma unroll
-      for (int c = 0; c < kPer; ++c) {
-        if (!has[c]) continue;
-        meta[c] = meta_base[slot[c]];
-        tr[c] = s.acc[0][slot[c]];
-        br[c] = s.acc[1][slot[c]];
-      }
-      // the running k-th best only changes in merge_candidates, i.e. between rounds
-      const float thr_f = s.thr_f;
-#pragma unroll
-      for (int c = 0; c < kPer; ++c) {
-        if (!has[c]) continue;
-        s.acc[0][slot[c]] = 0.0;
-        s.acc[1][slot[c]] = 0.0;
-        // screening (see finish_doc): sc_a/sc_t/sc_b fold the blend weights, 1/|q| and the x100
-        const float a = sc_a * meta[c].z;
-        const float b = tr[c] != 0.0 ? sc_t * ((float)tr[c] * meta[c].x) : 0.0f;
-        const float cc = br[c] != 0.0 ? sc_b * ((float)br[c] * meta[c].y) : 0.0f;
-        if ((a + b + cc) + (fabsf(a) + fabsf(b) + fabsf(cc)) * 1e-4f + 1e-30f < thr_f) continue;
-        finish_exact(p, s, q, d0 + slot[c], tr[c], br[c], qm, k);
-      }
-      __syncthreads();  // accumulators of this round are clean, candidates are complete
-      if (s.n_cand) merge_candidates(s, k);
-    }
-    list_done = list_end;
-  }
-  }
-  }
-
-  // this slab's list
-  __syncthreads();
-  const size_t base = ((size_t)q * p.n_slabs + slab) * k;
-  const uint32_t tb = s.top_buf, tn = s.top_n;
-  for (uint32_t j = tid; j < k; j += kT) {
-    if (j < tn) {
-      const uint32_t doc = s.top_doc[tb][j];
-      double sqd = 0.0;
-      if (p.sqd) {
-        sqd = p.sqd[doc];
-      } else if (p.probs) {
-        const double* pr = p.pr + (uint64_t)doc * p.T;
-        const double* pq = p.probs + (uint64_t)q * p.T;
-        for (uint32_t t = 0; t < p.T; ++t) sqd = __dadd_rn(sqd, __dmul_rn(pq[t], pr[t]));
-      }
-      p.part_doc[base + j] = doc;
-      p.part_final[base + j] = key_score(s.top_key[tb][j]);
-      p.part_pr[base + j] = sqd;
-    } else {
-      p.part_doc[base + j] = kNoDoc;
-      p.part_final[base + j] = 0.0;
-      p.part_pr[base + j] = 0.0;
-    }
-  }
-  if (tid == 0) {
-    p.part_count[(size_t)q * p.n_slabs + slab] = tn;
-    if (p.use_qthr && tn == k && s.top_key[tb][k - 1] > s.gkey) atomicMax(p.qthr + q, s.top_key[tb][k - 1]);
-  }
-  // stats: warp-reduce then one atomic per warp
-  for (int o = 16; o; o >>= 1) {
-    n_postings += __shfl_xor_sync(0xFFFFFFFFu, n_postings, o);
-    n_matched += __shfl_xor_sync(0xFFFFFFFFu, n_matched, o);
-  }
-  if ((tid & 31) == 0) {
-    if (n_postings) atomicAdd(p.stats, n_postings);
-    if (n_matched) atomicAdd(p.stats + 1, n_matched);
-  }
-}
+// The kernel itself lives in score_kernels.inc and is compiled once per token-limit variant.
+#define SS_LIM_NS lim_std
+#define SS_LIM_KW 64
+#define SS_LIM_PH 32
+#define SS_LIM_OCC 3
+#include "score_kernels.inc"
+#undef SS_LIM_NS
+#undef SS_LIM_KW
+#undef SS_LIM_PH
+#undef SS_LIM_OCC
+#define SS_LIM_NS lim_wide
+#define SS_LIM_KW 256
+#define SS_LIM_PH 256
+#define SS_LIM_OCC 2
+#define SS_LIM_WIDE 1
+#include "score_kernels.inc"
+#undef SS_LIM_NS
+#undef SS_LIM_KW
+#undef SS_LIM_PH
+#undef SS_LIM_OCC
+#undef SS_LIM_WIDE
+constexpr int kMaxKw = lim_std::kMaxKw, kMaxPh = lim_std::kMaxPh;
+constexpr int kWideKw = lim_wide::kMaxKw, kWidePh = lim_wide::kMaxPh;
 
 // Merge n_lists lists of up to k results per query into one, same total order.
 // in_*: [n_q][n_lists][k] (list_major == 0) or [n_lists][n_q][k] (list_major == 1).
@@ -1375,7 +150,8 @@ __global__ void __launch_bounds__(kT) k_merge(uint32_t n_lists, uint32_t k, uint
                                               const uint32_t* __restrict__ in_doc, const double* __restrict__ in_final,
                                               const double* __restrict__ in_pr, const uint32_t* __restrict__ in_count,
                                               uint32_t* __restrict__ out_doc, double* __restrict__ out_final,
-                                              double* __restrict__ out_pr, uint32_t* __restrict__ out_count) {
+                                              double* __restrict__ out_pr, uint32_t* __restrict__ out_count,
+                                              uint32_t doc_add) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint8_t* head = smem_raw;            // [n_lists] next unread entry of every list
   uint8_t* cnt = smem_raw + n_lists;   // [n_lists] entries of every list (<= k <= 128)
@@ -1445,7 +221,7 @@ __global__ void __launch_bounds__(kT) k_merge(uint32_t n_lists, uint32_t k, uint
       win_list = lst;
       if (lst != kNoDoc) {
         const size_t src = src_of(lst, head[lst]);
-        out_doc[(size_t)q * k + step] = doc;
+        out_doc[(size_t)q * k + step] = doc + doc_add;  // shard-local id -> global id (ss_index_set_doc_base)
         out_final[(size_t)q * k + step] = in_final[src];
         out_pr[(size_t)q * k + step] = in_pr[src];
         head[lst] = head[lst] + 1;
@@ -1745,40 +521,26 @@ static int build_dense_vectors(ss_engine* e, IndexState* ix, cudaStream_t st, ui
   return SS_OK;
 }
 
-extern "C" {
-
-SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, const uint32_t* kw_terms,
-                          const uint64_t* ph_ptr, const uint32_t* ph_terms, const double* topic_probs,
-                          int32_t probs_per_query, uint32_t k, uint32_t* out_doc, double* out_final, double* out_pr,
-                          uint32_t* out_count) {
-  SS_REQUIRE(e, SS_ERR_INVALID, "ss_score_batch: engine is NULL");
-  SS_REQUIRE(n_q == 0 || (kw_ptr && out_doc && out_final && out_pr && out_count), SS_ERR_INVALID,
-             "ss_score_batch: NULL argument");
-  SS_REQUIRE(k >= 1 && k <= (uint32_t)kMaxK, SS_ERR_INVALID, "ss_score_batch: k = %u, supported 1..%d", k, kMaxK);
-  SS_REQUIRE(n_q < 0x7FFFFFFFull, SS_ERR_INVALID, "ss_score_batch: batch too large");
-  if (n_q == 0) return SS_OK;
+// ss_score_batch / ss_score_batch_sharded.  sharded: after the local top-k every rank all-gathers the
+// [n_q][k] lists over NCCL and merges them with k_merge on its own stream, so
+// every rank returns the global top-k.
+// One batch whose queries all fit the chosen kernel variant (`wide`: lim_wide, accumulator path only).
+// Called with the engine lock held.
+static int score_batch_core(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, const uint32_t* kw_terms,
+                            const uint64_t* ph_ptr, const uint32_t* ph_terms, const double* topic_probs,
+                            int32_t probs_per_query, uint32_t k, uint32_t* out_doc, double* out_final, double* out_pr,
+                            uint32_t* out_count, bool sharded, bool wide) {
   const uint64_t n_kw = kw_ptr[n_q], n_ph = ph_ptr ? ph_ptr[n_q] : 0;
-  SS_REQUIRE((n_kw == 0 || kw_terms) && (n_ph == 0 || ph_terms), SS_ERR_INVALID, "ss_score_batch: NULL terms");
-  for (uint64_t q = 0; q < n_q; ++q) {
-    SS_REQUIRE(kw_ptr[q] <= kw_ptr[q + 1] && kw_ptr[q + 1] - kw_ptr[q] <= (uint64_t)kMaxKw, SS_ERR_INVALID,
-               "ss_score_batch: query %llu has a bad keyword range (max %d tokens)", (unsigned long long)q, kMaxKw);
-    if (ph_ptr) {
-      SS_REQUIRE(ph_ptr[q] <= ph_ptr[q + 1], SS_ERR_INVALID, "ss_score_batch: ph_ptr not monotone");
-      const uint64_t L = ph_ptr[q + 1] - ph_ptr[q];
-      // > 256 tokens can never match (uint8 TermPos, phrase.go:115); 33..256 would, but is not supported
-      SS_REQUIRE(L <= (uint64_t)kMaxPh || L > 256, SS_ERR_INVALID,
-                 "ss_score_batch: query %llu has a %llu-token phrase (max %d)", (unsigned long long)q,
-                 (unsigned long long)L, kMaxPh);
-    }
-  }
-  std::lock_guard<std::mutex> lock(e->mu);
-  DeviceGuard guard(e->device);
   IndexState* ix = e->idx;
   SS_REQUIRE(ix && (ix->tab[0].loaded || ix->tab[1].loaded), SS_ERR_STATE, "ss_score_batch: no index loaded");
   for (int tb = 0; tb < 2; ++tb)
     SS_REQUIRE(!ix->tab[tb].loaded || ix->tab[tb].has_mag, SS_ERR_STATE,
                "ss_score_batch: table %d has no doc norms (ss_term_weights / ss_set_doc_norms)", tb);
   const uint64_t D = ix->D;
+  SS_REQUIRE(D + ix->doc_base <= 0xFFFFFFFFull, SS_ERR_INVALID, "ss_score_batch: doc base %llu + %llu docs exceed 32 bit",
+             (unsigned long long)ix->doc_base, (unsigned long long)D);
+  const int world = sharded ? comm_world(e) : 1;
+  SS_REQUIRE((uint64_t)world * k <= (uint64_t)kMergeMax, SS_ERR_INVALID, "ss_score_batch_sharded: world * k too large");
   const bool blend = topic_probs != nullptr;
   if (blend) {
     SS_REQUIRE(ix->pr.p && ix->T > 0, SS_ERR_STATE, "ss_score_batch: topic_probs given but no PageRank set");
@@ -1838,6 +600,16 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   SS_TRY(ws_reserve(ws.out_count, n_q));
   SS_TRY(ws_reserve(ws.stats, 2));
   SS_TRY(ws_reserve(ws.qthr, n_q));
+  if (world > 1) {
+    SS_TRY(ws_reserve(ws.all_doc, (size_t)world * n_q * k));
+    SS_TRY(ws_reserve(ws.all_final, (size_t)world * n_q * k));
+    SS_TRY(ws_reserve(ws.all_pr, (size_t)world * n_q * k));
+    SS_TRY(ws_reserve(ws.all_count, (size_t)world * n_q));
+    SS_TRY(ws_reserve(ws.loc_doc, n_q * k));
+    SS_TRY(ws_reserve(ws.loc_final, n_q * k));
+    SS_TRY(ws_reserve(ws.loc_pr, n_q * k));
+    SS_TRY(ws_reserve(ws.loc_count, n_q));
+  }
   const uint64_t n_narrow = 2 * (n_kw + n_ph) * (n_slabs + 1);
   SS_TRY(ws_reserve(ws.narrow, n_narrow));
   // a table that was never loaded behaves as an empty one with zero norms
@@ -1859,8 +631,12 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
   if (timing)
     for (auto& x : ws.ev)
       if (!x) SS_CUDA(cudaEventCreate(&x));
-  SS_CUDA(cudaFuncSetAttribute(k_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  SS_CUDA(cudaFuncSetAttribute(k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  SS_CUDA(cudaFuncSetAttribute(lim_std::k_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(lim_std::Smem)));
+  SS_CUDA(cudaFuncSetAttribute(lim_std::k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(lim_std::Smem)));
+  SS_CUDA(cudaFuncSetAttribute(lim_wide::k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(lim_wide::Smem)));
 
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[0], st));
   SS_CUDA(cudaMemcpyAsync(ws.kw_ptr.p, kw_ptr, (n_q + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -1902,17 +678,19 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
     }
   }
   // impact vectors of the densest terms (SS_SCORE_DENSE=0 disables the path)
-  bool use_dense = true;
-  if (const char* env = getenv("SS_SCORE_DENSE")) use_dense = atoi(env) != 0;
+  bool use_dense = !wide;
+  if (const char* env = getenv("SS_SCORE_DENSE")) use_dense = use_dense && atoi(env) != 0;
   if (use_dense && D) SS_TRY(build_dense_vectors(e, ix, st, &launches));
 
   ScoreParams p{};
-  p.sort_max = kSortMax;
+  p.sort_max = lim_std::kSortMax;
   p.owner_path = 1;
   p.phrase_dense = 1;
   if (const char* env = getenv("SS_SCORE_PHRASE_DENSE")) p.phrase_dense = atoi(env);
   if (const char* env = getenv("SS_SCORE_OWNER")) p.owner_path = atoi(env);
-  if (const char* env = getenv("SS_SCORE_SORT_MAX")) p.sort_max = std::min<uint32_t>(kSortMax, (uint32_t)atoi(env));
+  if (const char* env = getenv("SS_SCORE_SORT_MAX"))
+    p.sort_max = std::min<uint32_t>(lim_std::kSortMax, (uint32_t)atoi(env));
+  if (wide) p.sort_max = 0;  // the sparse paths tag postings with an 8-bit list number: accumulator path only
   p.meta32 = ix->meta32.p;
   p.tab[0] = view_of(ix->tab[0]);
   p.tab[1] = view_of(ix->tab[1]);
@@ -1964,18 +742,39 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
     ++launches;
   }
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[1], st));
-  if (n_ph) k_score<true><<<(unsigned)(n_q * n_slabs), kT, sizeof(Smem), st>>>(p);
-  else k_score<false><<<(unsigned)(n_q * n_slabs), kT, sizeof(Smem), st>>>(p);
+  if (wide) lim_wide::k_score<true><<<(unsigned)(n_q * n_slabs), kT, sizeof(lim_wide::Smem), st>>>(p);
+  else if (n_ph) lim_std::k_score<true><<<(unsigned)(n_q * n_slabs), kT, sizeof(lim_std::Smem), st>>>(p);
+  else lim_std::k_score<false><<<(unsigned)(n_q * n_slabs), kT, sizeof(lim_std::Smem), st>>>(p);
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[2], st));
   k_merge<<<(unsigned)n_q, kT, (size_t)n_slabs * 2, st>>>((uint32_t)n_slabs, k, (uint32_t)n_q, 0, ws.part_doc.p,
                                                               ws.part_final.p, ws.part_pr.p, ws.part_count.p,
                                                               ws.out_doc.p, ws.out_final.p, ws.out_pr.p,
-                                                              ws.out_count.p);
+                                                              ws.out_count.p, (uint32_t)ix->doc_base);
   launches += 2;
-  SS_CUDA(cudaMemcpyAsync(out_doc, ws.out_doc.p, n_q * k * 4, cudaMemcpyDeviceToHost, st));
-  SS_CUDA(cudaMemcpyAsync(out_final, ws.out_final.p, n_q * k * 8, cudaMemcpyDeviceToHost, st));
-  SS_CUDA(cudaMemcpyAsync(out_pr, ws.out_pr.p, n_q * k * 8, cudaMemcpyDeviceToHost, st));
-  SS_CUDA(cudaMemcpyAsync(out_count, ws.out_count.p, n_q * 4, cudaMemcpyDeviceToHost, st));
+  const uint32_t* r_doc = ws.out_doc.p;
+  const double *r_final = ws.out_final.p, *r_pr = ws.out_pr.p;
+  const uint32_t* r_count = ws.out_count.p;
+  if (timing) SS_CUDA(cudaEventRecord(ws.ev[4], st));
+  if (world > 1) {
+    // doc-sharded index: every rank contributes its local top-k (already global doc ids) and merges all
+    // of them with the same comparator
+    const void* in[4] = {ws.out_doc.p, ws.out_final.p, ws.out_pr.p, ws.out_count.p};
+    void* all[4] = {ws.all_doc.p, ws.all_final.p, ws.all_pr.p, ws.all_count.p};
+    const size_t bytes[4] = {n_q * k * 4, n_q * k * 8, n_q * k * 8, n_q * 4};
+    SS_TRY(comm_allgather_dev(e, 4, in, all, bytes));
+    k_merge<<<(unsigned)n_q, kT, (size_t)world * 2, st>>>((uint32_t)world, k, (uint32_t)n_q, 1, ws.all_doc.p,
+                                                             ws.all_final.p, ws.all_pr.p, ws.all_count.p, ws.loc_doc.p,
+                                                             ws.loc_final.p, ws.loc_pr.p, ws.loc_count.p, 0u);
+    ++launches;
+    r_doc = ws.loc_doc.p;
+    r_final = ws.loc_final.p;
+    r_pr = ws.loc_pr.p;
+    r_count = ws.loc_count.p;
+  }
+  SS_CUDA(cudaMemcpyAsync(out_doc, r_doc, n_q * k * 4, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(out_final, r_final, n_q * k * 8, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(out_pr, r_pr, n_q * k * 8, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(out_count, r_count, n_q * 4, cudaMemcpyDeviceToHost, st));
   unsigned long long h_stats[2] = {0, 0};
   SS_CUDA(cudaMemcpyAsync(h_stats, ws.stats.p, 16, cudaMemcpyDeviceToHost, st));
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[3], st));
@@ -1994,8 +793,117 @@ SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, co
     ix->stats.kernel_ms = ms;
     cudaEventElapsedTime(&ms, ws.ev[1], ws.ev[2]);
     ix->stats.score_kernel_ms = ms;
+    cudaEventElapsedTime(&ms, ws.ev[4], ws.ev[3]);  // cross-shard all-gather + merge + D2H of the results
+    ix->stats.shard_merge_ms = ms;
   }
   return SS_OK;
+}
+
+// Validates the batch and routes it: queries within the standard limits (64 keyword tokens, 32 phrase tokens)
+// go through lim_std in one launch; the rare over-long ones (up to 256 / 256; the reference evaluates phrases
+// of up to 256 tokens, retrieval/phrase.go:111-118) are scored as a second sub-batch by lim_wide and their
+// rows scattered back, so one such query no longer fails everybody else's.
+static int score_batch_entry(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, const uint32_t* kw_terms,
+                             const uint64_t* ph_ptr, const uint32_t* ph_terms, const double* topic_probs,
+                             int32_t probs_per_query, uint32_t k, uint32_t* out_doc, double* out_final,
+                             double* out_pr, uint32_t* out_count, bool sharded) {
+  SS_REQUIRE(e, SS_ERR_INVALID, "ss_score_batch: engine is NULL");
+  SS_REQUIRE(n_q == 0 || (kw_ptr && out_doc && out_final && out_pr && out_count), SS_ERR_INVALID,
+             "ss_score_batch: NULL argument");
+  SS_REQUIRE(k >= 1 && k <= (uint32_t)kMaxK, SS_ERR_INVALID, "ss_score_batch: k = %u, supported 1..%d", k, kMaxK);
+  SS_REQUIRE(n_q < 0x7FFFFFFFull, SS_ERR_INVALID, "ss_score_batch: batch too large");
+  if (n_q == 0) return SS_OK;
+  const uint64_t n_kw = kw_ptr[n_q], n_ph = ph_ptr ? ph_ptr[n_q] : 0;
+  SS_REQUIRE((n_kw == 0 || kw_terms) && (n_ph == 0 || ph_terms), SS_ERR_INVALID, "ss_score_batch: NULL terms");
+  std::vector<uint64_t> wide_q;
+  for (uint64_t q = 0; q < n_q; ++q) {
+    SS_REQUIRE(kw_ptr[q] <= kw_ptr[q + 1], SS_ERR_INVALID, "ss_score_batch: kw_ptr not monotone at query %llu",
+               (unsigned long long)q);
+    const uint64_t nk = kw_ptr[q + 1] - kw_ptr[q];
+    SS_REQUIRE(nk <= (uint64_t)kWideKw, SS_ERR_INVALID, "ss_score_batch: query %llu has %llu keyword tokens (max %d)",
+               (unsigned long long)q, (unsigned long long)nk, kWideKw);
+    uint64_t L = 0;
+    if (ph_ptr) {
+      SS_REQUIRE(ph_ptr[q] <= ph_ptr[q + 1], SS_ERR_INVALID, "ss_score_batch: ph_ptr not monotone");
+      L = ph_ptr[q + 1] - ph_ptr[q];
+    }
+    // a phrase of more than 256 tokens can never match (uint8 TermPos, phrase.go:115): the kernel drops it
+    // (its tokens still count in queryLength, main_retrieve.go:90)
+    if (nk > (uint64_t)kMaxKw || (L > (uint64_t)kMaxPh && L <= (uint64_t)kWidePh)) wide_q.push_back(q);
+  }
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  if (wide_q.empty())
+    return score_batch_core(e, n_q, kw_ptr, kw_terms, ph_ptr, ph_terms, topic_probs, probs_per_query, k, out_doc,
+                            out_final, out_pr, out_count, sharded, false);
+  // split: sub-batch 0 = standard queries, sub-batch 1 = wide queries
+  IndexState* ix = e->idx;
+  const uint32_t T = ix ? ix->T : 0;
+  ss_score_stats total{};
+  size_t wi = 0;
+  std::vector<uint64_t> members[2];
+  for (uint64_t q = 0; q < n_q; ++q) {
+    const bool w = wi < wide_q.size() && wide_q[wi] == q;
+    if (w) ++wi;
+    members[w ? 1 : 0].push_back(q);
+  }
+  for (int part = 0; part < 2; ++part) {
+    const std::vector<uint64_t>& m = members[part];
+    if (m.empty()) continue;
+    const uint64_t nq = m.size();
+    std::vector<uint64_t> s_kw_ptr(nq + 1, 0), s_ph_ptr(nq + 1, 0);
+    std::vector<uint32_t> s_kw, s_ph;
+    std::vector<double> s_probs;
+    for (uint64_t i = 0; i < nq; ++i) {
+      const uint64_t q = m[i];
+      s_kw.insert(s_kw.end(), kw_terms + kw_ptr[q], kw_terms + kw_ptr[q + 1]);
+      s_kw_ptr[i + 1] = s_kw.size();
+      if (ph_ptr) s_ph.insert(s_ph.end(), ph_terms + ph_ptr[q], ph_terms + ph_ptr[q + 1]);
+      s_ph_ptr[i + 1] = s_ph.size();
+      if (topic_probs && probs_per_query) s_probs.insert(s_probs.end(), topic_probs + q * T, topic_probs + (q + 1) * T);
+    }
+    std::vector<uint32_t> o_doc(nq * k), o_cnt(nq);
+    std::vector<double> o_fin(nq * k), o_pr(nq * k);
+    const double* probs = topic_probs ? (probs_per_query ? s_probs.data() : topic_probs) : nullptr;
+    SS_TRY(score_batch_core(e, nq, s_kw_ptr.data(), s_kw.data(), ph_ptr ? s_ph_ptr.data() : nullptr, s_ph.data(), probs,
+                            probs_per_query, k, o_doc.data(), o_fin.data(), o_pr.data(), o_cnt.data(), sharded,
+                            part == 1));
+    for (uint64_t i = 0; i < nq; ++i) {
+      const uint64_t q = m[i];
+      memcpy(out_doc + q * k, o_doc.data() + i * k, k * 4);
+      memcpy(out_final + q * k, o_fin.data() + i * k, k * 8);
+      memcpy(out_pr + q * k, o_pr.data() + i * k, k * 8);
+      out_count[q] = o_cnt[i];
+    }
+    const ss_score_stats& st = e->idx->stats;
+    total.postings_scanned += st.postings_scanned;
+    total.docs_matched += st.docs_matched;
+    total.algorithmic_bytes += st.algorithmic_bytes;
+    total.launches += st.launches;
+    total.kernel_ms += st.kernel_ms;
+    total.score_kernel_ms += st.score_kernel_ms;
+    total.shard_merge_ms += st.shard_merge_ms;
+  }
+  e->idx->stats = total;
+  return SS_OK;
+}
+
+extern "C" {
+
+SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, const uint32_t* kw_terms,
+                          const uint64_t* ph_ptr, const uint32_t* ph_terms, const double* topic_probs,
+                          int32_t probs_per_query, uint32_t k, uint32_t* out_doc, double* out_final, double* out_pr,
+                          uint32_t* out_count) {
+  return score_batch_entry(e, n_q, kw_ptr, kw_terms, ph_ptr, ph_terms, topic_probs, probs_per_query, k, out_doc,
+                           out_final, out_pr, out_count, false);
+}
+
+SS_API int ss_score_batch_sharded(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, const uint32_t* kw_terms,
+                                  const uint64_t* ph_ptr, const uint32_t* ph_terms, const double* topic_probs,
+                                  int32_t probs_per_query, uint32_t k, uint32_t* out_doc, double* out_final,
+                                  double* out_pr, uint32_t* out_count) {
+  return score_batch_entry(e, n_q, kw_ptr, kw_terms, ph_ptr, ph_terms, topic_probs, probs_per_query, k, out_doc,
+                           out_final, out_pr, out_count, true);
 }
 
 SS_API int ss_merge_topk(ss_engine* e, uint32_t n_lists, uint64_t n_q, uint32_t k, const uint32_t* docs,
@@ -2004,7 +912,9 @@ SS_API int ss_merge_topk(ss_engine* e, uint32_t n_lists, uint64_t n_q, uint32_t 
   SS_REQUIRE(e, SS_ERR_INVALID, "ss_merge_topk: engine is NULL");
   SS_REQUIRE(n_q == 0 || (docs && finals && prs && counts && out_doc && out_final && out_pr && out_count),
              SS_ERR_INVALID, "ss_merge_topk: NULL argument");
-  SS_REQUIRE(n_lists >= 1 && k >= 1 && (uint64_t)n_lists * k <= (uint64_t)kMergeMax, SS_ERR_INVALID,
+  // k_merge keeps each list's head and length in one byte: k <= kMaxK (128), as in ss_score_batch
+  SS_REQUIRE(k >= 1 && k <= (uint32_t)kMaxK, SS_ERR_INVALID, "ss_merge_topk: k = %u, supported 1..%d", k, kMaxK);
+  SS_REQUIRE(n_lists >= 1 && (uint64_t)n_lists * k <= (uint64_t)kMergeMax, SS_ERR_INVALID,
              "ss_merge_topk: n_lists * k = %llu, max %d", (unsigned long long)n_lists * k, kMergeMax);
   if (n_q == 0) return SS_OK;
   std::lock_guard<std::mutex> lock(e->mu);
@@ -2026,7 +936,7 @@ SS_API int ss_merge_topk(ss_engine* e, uint32_t n_lists, uint64_t n_q, uint32_t 
   SS_CUDA(cudaMemcpyAsync(d_pr.p, prs, n * 8, cudaMemcpyHostToDevice, st));
   SS_CUDA(cudaMemcpyAsync(d_cnt.p, counts, (size_t)n_lists * n_q * 4, cudaMemcpyHostToDevice, st));
   k_merge<<<(unsigned)n_q, kT, (size_t)n_lists * 2, st>>>(n_lists, k, (uint32_t)n_q, 1, d_doc.p, d_fin.p, d_pr.p,
-                                                              d_cnt.p, o_doc.p, o_fin.p, o_pr.p, o_cnt.p);
+                                                              d_cnt.p, o_doc.p, o_fin.p, o_pr.p, o_cnt.p, 0u);
   SS_CUDA(cudaMemcpyAsync(out_doc, o_doc.p, n_q * k * 4, cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaMemcpyAsync(out_final, o_fin.p, n_q * k * 8, cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaMemcpyAsync(out_pr, o_pr.p, n_q * k * 8, cudaMemcpyDeviceToHost, st));

@@ -289,3 +289,112 @@ def test_invalid_arguments(engine):
         engine.score_batch([0, 1], [0], k=129)
     with pytest.raises(capi.SSError):  # blend without PageRank
         engine.score_batch([0, 1], [0], topic_probs=np.ones(4), k=5)
+
+
+# ---- round 2: over-long queries, shard-local doc ids, in-engine shard merge --------------------
+def _small_index(engine, V=300, D=3000, seed=43):
+    tabs = {}
+    engine.index_clear()
+    engine.set_pagerank(None)
+    for tid in (capi.SS_TITLE, capi.SS_BODY):
+        t = synth.index_table(V, D, tid, postings_per_doc=30.0 if tid else 6.0, with_positions=True, seed=seed)
+        engine.index_load(tid, D, t.term_ptr, t.doc_ids, t.norm_tf, t.pos_ptr, t.pos)
+        w, mag = engine.term_weights(tid, float(D), t.n_postings, D)
+        tabs[tid] = (O.Table(t.term_ptr, t.doc_ids, w, t.pos_ptr, t.pos), mag, t)
+    return tabs
+
+
+def test_over_long_queries_are_served_per_query(engine):
+    """A 33..256-token phrase or > 64 keyword tokens used to fail the whole batch (ADVICE round 1,
+    score.cu:1763); the reference evaluates them (phrase.go:111-118).  They take the wide kernel variant,
+    everybody else's rows are unchanged."""
+    V, D = 300, 3000
+    tabs = _small_index(engine, V, D)
+    rng = np.random.default_rng(5)
+    body = tabs[capi.SS_BODY][2]
+    # a phrase that really occurs: consecutive positions do not exist in the synthetic index, so build the
+    # long phrase from one doc's terms anyway (it must evaluate, matching or not), plus repeated-token phrases
+    kws = [[1, 2], list(rng.integers(0, V, 100)), [3], list(rng.integers(0, V, 65)), [5, 5, 7], list(range(0, 256))]
+    phs = [[], [], list(rng.integers(0, V, 40)), [4, 4], [], list(rng.integers(0, 8, 256))]
+    kw_ptr, kw, ph_ptr, ph = queries_csr(kws, phs)
+    pr = np.random.default_rng(6).random((D, 4)) * 1e-3
+    for probs in (None, np.full(4, 0.25)):
+        engine.set_pagerank(None if probs is None else pr)
+        got = engine.score_batch(kw_ptr, kw, ph_ptr, ph, topic_probs=probs, k=10)
+        exp = O.score_batch(tabs[0][0], tabs[1][0], D, tabs[0][1], tabs[1][1], None if probs is None else pr, kw_ptr,
+                            kw, ph_ptr, ph, topic_probs=probs, k=10)
+        assert_same_results(got, exp)
+        assert got[3][1] > 0 and got[3][5] > 0
+    # beyond the wide limits the call still fails, naming the query
+    kw_ptr, kw, ph_ptr, ph = queries_csr([[1], list(range(257))], [[], []])
+    with pytest.raises(capi.SSError) as ei:
+        engine.score_batch(kw_ptr, kw, ph_ptr, ph, k=10)
+    assert "query 1" in str(ei.value)
+    # a phrase of more than 256 tokens can never match (uint8 TermPos): evaluated as "no phrase hit"
+    kw_ptr, kw, ph_ptr, ph = queries_csr([[1, 2]], [list(rng.integers(0, V, 300))])
+    engine.set_pagerank(None)
+    got = engine.score_batch(kw_ptr, kw, ph_ptr, ph, k=10)
+    exp = O.score_batch(tabs[0][0], tabs[1][0], D, tabs[0][1], tabs[1][1], None, kw_ptr, kw, ph_ptr, ph, k=10)
+    assert_same_results(got, exp)
+
+
+def test_merge_topk_rejects_k_above_128(engine):
+    docs = np.zeros((2, 1, 129), np.uint32)
+    with pytest.raises(capi.SSError):
+        engine.merge_topk(docs, np.zeros((2, 1, 129)), np.zeros((2, 1, 129)), np.zeros((2, 1), np.uint32))
+
+
+def test_doc_base_and_local_ids(engine):
+    """A shard loaded under local ids + ss_index_set_doc_base returns the same global result rows as the
+    same shard loaded under global ids (round 1 layout)."""
+    V, D, lo, hi = 400, 6000, 2000, 4500
+    rng = np.random.default_rng(11)
+    pr = rng.random((D, 8)) * 1e-4
+    probs = rng.random(8)
+    q = synth.queries(200, V, phrase_fraction=0.3, seed=9)
+    res = []
+    for local in (False, True):
+        engine.index_clear()
+        engine.index_set_doc_base(lo if local else 0)
+        for tid in (capi.SS_TITLE, capi.SS_BODY):
+            t = synth.index_table(V, D, tid, postings_per_doc=30.0 if tid else 6.0, doc_lo=lo, doc_hi=hi,
+                                  with_positions=True)
+            ids = t.doc_ids - np.uint32(lo) if local else t.doc_ids
+            nd = hi - lo if local else D
+            engine.index_load(tid, nd, t.term_ptr, ids, t.norm_tf, t.pos_ptr, t.pos)
+            engine.term_weights(tid, float(D), t.n_postings, nd, df_global=t.df_global, want=False)
+        engine.set_pagerank(pr[lo:hi] if local else pr)
+        res.append(engine.score_batch(q.kw_ptr, q.kw_terms, q.ph_ptr, q.ph_terms, topic_probs=probs, k=10))
+        # without a communicator the sharded entry is the plain one
+        res.append(engine.score_batch(q.kw_ptr, q.kw_terms, q.ph_ptr, q.ph_terms, topic_probs=probs, k=10,
+                                      sharded=True))
+    engine.index_clear()
+    engine.index_set_doc_base(0)
+    for r in res[1:]:
+        for a, b in zip(res[0], r):
+            assert np.array_equal(a, b, equal_nan=True)
+    assert (res[0][3] > 0).any() and res[0][0][res[0][0] != 0xFFFFFFFF].min() >= lo
+
+
+def test_reload_with_more_docs_refreshes_blend_cache(engine):
+    """ADVICE round 1 (index.cu:217): the cached blend vector must not survive a reload with a larger D."""
+    V = 200
+    rng = np.random.default_rng(3)
+    probs = np.full(4, 0.25)
+    q = synth.queries(64, V, seed=2)
+    for D in (1000, 5000):
+        engine.index_clear() if D == 1000 else None
+        tabs = {}
+        for tid in (capi.SS_BODY, capi.SS_TITLE):
+            t = synth.index_table(V, D, tid, postings_per_doc=20.0 if tid else 5.0)
+            if D == 5000 and tid == capi.SS_BODY:
+                engine.index_clear()
+            engine.index_load(tid, D, t.term_ptr, t.doc_ids, t.norm_tf)
+            w, mag = engine.term_weights(tid, float(D), t.n_postings, D)
+            tabs[tid] = (O.Table(t.term_ptr, t.doc_ids, w), mag)
+        pr = rng.random((D, 4)) * 1e-3
+        engine.set_pagerank(pr)
+        got = engine.score_batch(q.kw_ptr, q.kw_terms, topic_probs=probs, k=10)
+        exp = O.score_batch(tabs[0][0], tabs[1][0], D, tabs[0][1], tabs[1][1], pr, q.kw_ptr, q.kw_terms,
+                            topic_probs=probs, k=10)
+        assert_same_results(got, exp)
