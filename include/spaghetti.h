@@ -84,6 +84,16 @@ SS_API int ss_comm_init(ss_engine* e, const void* id128, int32_t rank, int32_t w
 SS_API int ss_graph_load_csr(ss_engine* e, uint64_t n_nodes, uint64_t n_edges,
                              const uint64_t* row_ptr, const uint32_t* col_idx);
 
+/* Sharded export for a multi-GPU engine group: every rank of the ss_comm_init group passes the slice
+ * [row_lo, row_hi) of the same CSR that it exported (row_ptr [row_hi - row_lo + 1] local to the slice,
+ * starting at 0; col_idx holds global child ids).  The slices tile [0, n_nodes); for the best gather order
+ * they should ascend with the rank.  The ranks exchange edges once over NVLink so that each keeps exactly
+ * the in-edges of the rows it owns: host-to-device bytes and sort work per rank are 1/world of
+ * ss_graph_load_csr, which every rank would have to call with the whole graph.  Collective: every rank of
+ * the group must call it.  With no communicator it is ss_graph_load_csr. */
+SS_API int ss_graph_load_csr_rows(ss_engine* e, uint64_t n_nodes, uint64_t row_lo, uint64_t row_hi,
+                                  const uint64_t* row_ptr, const uint32_t* col_idx);
+
 /* One power-iteration run per topic (pagerank.go:54-63), all topics advanced
  * together as columns of one SpMM; topic t starts from 1/num_pages[t]
  * (pagerank.go:61,104-105) and stops on its own when its L1 change <= eps
@@ -96,6 +106,13 @@ SS_API int ss_graph_load_csr(ss_engine* e, uint64_t n_nodes, uint64_t n_edges,
 SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topics,
                        const int64_t* num_pages, uint32_t max_iters, double* out_rank,
                        uint32_t* out_iters);
+/* Extension beyond the reference as shipped (README.md:9 promises it, ranking/pagerank.go:90,117
+ * teleports uniformly): per-topic teleport vectors.  weight is [n_nodes][n_topics] row major with
+ * weight[v][t] = n_nodes * v_t[v] for a teleport distribution v_t over the nodes (sum_v v_t[v] = 1), so that
+ * all ones is the reference's uniform teleport: cur[v] = (inherited + (1-d) * weight[v][t]) / Tot, Tot unchanged.
+ * Applies to the following ss_pagerank calls with the same n_topics until the next graph load; NULL resets.
+ * Call after the graph load (a rank keeps the weights of the rows it owns). */
+SS_API int ss_pagerank_set_teleport(ss_engine* e, uint64_t n_nodes, uint32_t n_topics, const double* weight);
 /* Copy the last result, rows [row_lo, row_hi), to host. */
 SS_API int ss_pagerank_fetch(ss_engine* e, uint64_t row_lo, uint64_t row_hi, double* out_rank);
 
@@ -107,9 +124,11 @@ typedef struct ss_pagerank_stats {
   uint32_t launches;           /* kernels launched by the last ss_pagerank */
   double sweep_ms_total;       /* device time in sweep kernels (SS_FLAG_TIMING) */
   double gather_ms_total;      /* device time of the two gather kernels only */
-  double exchange_ms_total;    /* device time in the per-sweep NVLink exchange */
+  double exchange_ms_total;    /* device time the sweep loop waits for the NVLink exchange after its own
+                                  kernels (the exposed part; the rest overlaps the sweep) */
   double load_ms;              /* last ss_graph_load_csr, host wall clock */
   double short_ms_total;       /* device time of the short-row kernel only (SS_FLAG_TIMING) */
+  double exchange_busy_ms_total; /* exchange stream: first chunk broadcast .. end of the all-reduce, per sweep summed */
 } ss_pagerank_stats;
 SS_API int ss_pagerank_get_stats(ss_engine* e, ss_pagerank_stats* out);
 
@@ -199,6 +218,9 @@ typedef struct ss_score_stats {
   double score_kernel_ms;      /* device time of the dominant scoring kernel */
   double shard_merge_ms;       /* device time from the end of the local merge to the end of the result copies
                                   (ss_score_batch_sharded: NCCL all-gather + cross-shard merge + D2H) */
+  uint64_t model_bytes;        /* bytes the batch has to move on the path it takes: a query with a dense keyword
+                                  streams 2 B per doc per dense token (+ the blend bound) and reads 8 B per posting
+                                  of its other tokens; other queries read 8 B per posting; + 12 B per result */
 } ss_score_stats;
 SS_API int ss_score_get_stats(ss_engine* e, ss_score_stats* out);
 

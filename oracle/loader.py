@@ -57,6 +57,9 @@ def lib():
                                                C.c_double, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32,
                                                C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         L.oracle_pagerank_fair_csc.restype = C.c_int
+        L.oracle_pagerank_biased.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_uint32,
+                                             C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_pagerank_biased.restype = C.c_int
         L.oracle_term_weights.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_double, C.c_void_p, C.c_void_p]
         L.oracle_term_weights.restype = C.c_int
@@ -137,6 +140,23 @@ def csc_build(row_ptr, col_idx):
     in_src = np.zeros(max(1, len(col_idx)), dtype=np.uint32)
     assert lib().oracle_csc_build(n, _p(row_ptr), _p(col_idx), _p(in_ptr), _p(in_src)) == 0
     return in_ptr, in_src
+
+
+def pagerank_biased(row_ptr, col_idx, damping, eps, num_pages, tele_w, max_iters=0, n_threads=0):
+    """Extension: per-topic teleport weights tele_w [N][T] = N * v_t[v] -> (rank, iters)."""
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint64)
+    col_idx = np.ascontiguousarray(col_idx, dtype=np.uint32)
+    num_pages = np.ascontiguousarray(num_pages, dtype=np.int64)
+    tele_w = np.ascontiguousarray(tele_w, dtype=np.float64)
+    n, t = len(row_ptr) - 1, len(num_pages)
+    assert tele_w.shape == (n, t)
+    rank = np.zeros((n, t), dtype=np.float64)
+    iters = np.zeros(t, dtype=np.uint32)
+    rc = lib().oracle_pagerank_biased(n, _p(row_ptr), _p(col_idx), damping, eps, t, _p(num_pages), max_iters,
+                                      n_threads, _p(tele_w), _p(rank), _p(iters))
+    if rc != 0:
+        raise RuntimeError(f"oracle_pagerank_biased failed: {rc}")
+    return rank, iters
 
 
 def pagerank_fair_csc(row_ptr, in_ptr, in_src, damping, eps, num_pages, max_iters=0, fixed_iters=0,

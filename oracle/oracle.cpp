@@ -197,12 +197,15 @@ extern "C" int oracle_csc_build(uint64_t n_nodes, const uint64_t* row_ptr, const
   return 0;
 }
 
-extern "C" int oracle_pagerank_fair_csc(uint64_t n_nodes, const uint64_t* row_ptr, const uint64_t* in_ptr,
-                                        const uint32_t* in_src, double damping, double eps,
-                                        uint32_t n_topics, const int64_t* num_pages,
-                                        uint32_t max_iters, uint32_t fixed_iters, int n_threads,
-                                        double* out_rank, uint32_t* out_iters,
-                                        double* sweep_seconds) {
+// tele_w: NULL = the reference's uniform teleport (pagerank.go:90,117: every node gets 1-d); else [N][T]
+// weights N * v_t[v] of a per-topic teleport vector v_t (sum_v v_t[v] = 1), SURVEY.md 8(f)-4: node v of topic
+// t gets (1-d) * tele_w[v][t] instead, Tot is unchanged because the weights of a topic sum to N.
+static int pagerank_fair_csc_impl(uint64_t n_nodes, const uint64_t* row_ptr, const uint64_t* in_ptr,
+                                  const uint32_t* in_src, double damping, double eps,
+                                  uint32_t n_topics, const int64_t* num_pages,
+                                  uint32_t max_iters, uint32_t fixed_iters, int n_threads,
+                                  const double* tele_w, double* out_rank, uint32_t* out_iters,
+                                  double* sweep_seconds) {
   const uint64_t N = n_nodes;
   const uint32_t T = n_topics;
   if (n_threads <= 0) n_threads = omp_get_max_threads();
@@ -256,7 +259,7 @@ extern "C" int oracle_pagerank_fair_csc(uint64_t n_nodes, const uint64_t* row_pt
             cur[v * T + t] = last[v * T + t];
             continue;
           }
-          double r = (acc[t] + teleport) / tot[t];
+          double r = (acc[t] + (tele_w ? teleport * tele_w[v * T + t] : teleport)) / tot[t];
           cur[v * T + t] = r;
           d_loc[t] += std::fabs(r - last[v * T + t]);
         }
@@ -278,6 +281,27 @@ extern "C" int oracle_pagerank_fair_csc(uint64_t n_nodes, const uint64_t* row_pt
   return 0;
 }
 
+extern "C" int oracle_pagerank_fair_csc(uint64_t n_nodes, const uint64_t* row_ptr, const uint64_t* in_ptr,
+                                        const uint32_t* in_src, double damping, double eps,
+                                        uint32_t n_topics, const int64_t* num_pages,
+                                        uint32_t max_iters, uint32_t fixed_iters, int n_threads,
+                                        double* out_rank, uint32_t* out_iters,
+                                        double* sweep_seconds) {
+  return pagerank_fair_csc_impl(n_nodes, row_ptr, in_ptr, in_src, damping, eps, n_topics, num_pages, max_iters,
+                                fixed_iters, n_threads, nullptr, out_rank, out_iters, sweep_seconds);
+}
+// Extension (not in the reference as shipped): genuinely topic-biased teleport, README.md:9 / SURVEY.md 8(f)-4.
+extern "C" int oracle_pagerank_biased(uint64_t n_nodes, const uint64_t* row_ptr, const uint32_t* col_idx,
+                                      double damping, double eps, uint32_t n_topics,
+                                      const int64_t* num_pages, uint32_t max_iters, int n_threads,
+                                      const double* tele_w, double* out_rank, uint32_t* out_iters) {
+  const uint64_t N = n_nodes, E = row_ptr[N];
+  std::vector<uint64_t> in_ptr(N + 1);
+  std::vector<uint32_t> in_src(E ? E : 1);
+  oracle_csc_build(N, row_ptr, col_idx, in_ptr.data(), in_src.data());
+  return pagerank_fair_csc_impl(N, row_ptr, in_ptr.data(), in_src.data(), damping, eps, n_topics, num_pages,
+                                max_iters, 0, n_threads, tele_w, out_rank, out_iters, nullptr);
+}
 extern "C" int oracle_pagerank_fair(uint64_t n_nodes, const uint64_t* row_ptr,
                                     const uint32_t* col_idx, double damping, double eps,
                                     uint32_t n_topics, const int64_t* num_pages,

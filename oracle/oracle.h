@@ -60,6 +60,12 @@ int oracle_pagerank_fair(uint64_t n_nodes, const uint64_t* row_ptr, const uint32
  * arm on a prebuilt CSC. in_ptr is [n_nodes+1], in_src is [n_edges]. */
 int oracle_csc_build(uint64_t n_nodes, const uint64_t* row_ptr, const uint32_t* col_idx,
                      uint64_t* in_ptr, uint32_t* in_src);
+/* Extension beyond the shipped reference (README.md:9): per-topic teleport vectors.
+ * tele_w [N][T] = N * v_t[v]; all ones reproduces oracle_pagerank_fair. */
+int oracle_pagerank_biased(uint64_t n_nodes, const uint64_t* row_ptr, const uint32_t* col_idx,
+                           double damping, double eps, uint32_t n_topics, const int64_t* num_pages,
+                           uint32_t max_iters, int n_threads, const double* tele_w, double* out_rank,
+                           uint32_t* out_iters);
 int oracle_pagerank_fair_csc(uint64_t n_nodes, const uint64_t* row_ptr, const uint64_t* in_ptr,
                              const uint32_t* in_src, double damping, double eps, uint32_t n_topics,
                              const int64_t* num_pages, uint32_t max_iters, uint32_t fixed_iters,

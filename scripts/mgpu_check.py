@@ -14,26 +14,40 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 eng = capi.Engine(device=local, timing=True)
 eng.comm_init(sharding.share_unique_id(capi.comm_unique_id), rank, world)
 
-# ---- HP-1
+# ---- HP-1: every load / exchange combination against the oracle
 N, E = 300000, 4000000
 lo, hi = sharding.row_slice(rank, world, N)
 part = synth.graph_rows(N, E, lo, hi, seed=42, n_threads=4)
 row_ptr, col_idx = sharding.assemble_graph(N, part.row_ptr, part.col_idx, device="cuda")
 npg = synth.topics(16)
-eng.graph_load_csr(row_ptr, col_idx)
-rank_all, iters, status = eng.pagerank(0.75, 1e-9, npg)
-st = eng.pagerank_stats()
 ref, it_ref, _ = O.pagerank_fair(row_ptr, col_idx, 0.75, 1e-9, npg, n_threads=4)
-l1 = np.abs(rank_all - ref).sum(axis=0).max()
-own = eng.pagerank_fetch(int(st.row_lo), int(st.row_lo + st.local_rows))
-ok_pr = (status == 0 and iters.tolist() == it_ref.tolist() and l1 <= 1e-9 and
-         np.array_equal(own, rank_all[int(st.row_lo): int(st.row_lo + st.local_rows)]))
+ok_pr = True
+for load, env in (("full", {}), ("rows", {}), ("rows", {"SS_PR_EXCHANGE": "nccl", "SS_PR_CHUNKS": "4"}),
+                  ("full", {"SS_PR_EXCHANGE": "nccl", "SS_PR_CHUNKS": "3"}), ("rows", {"SS_PR_EXCHANGE": "nccl"})):
+    os.environ.update(env)
+    if load == "full":
+        eng.graph_load_csr(row_ptr, col_idx)
+    else:  # sharded export: this rank's slice only
+        eng.graph_load_csr_rows(N, lo, hi, part.row_ptr, part.col_idx)
+    for n_t in (16, 8):
+        rank_all, iters, status = eng.pagerank(0.75, 1e-9, npg[:n_t])
+        st = eng.pagerank_stats()
+        l1 = np.abs(rank_all - ref[:, :n_t]).sum(axis=0).max()
+        own = eng.pagerank_fetch(int(st.row_lo), int(st.row_lo + st.local_rows))
+        ok = (status == 0 and iters.tolist() == it_ref[:n_t].tolist() and l1 <= 1e-9 and
+              np.array_equal(own, rank_all[int(st.row_lo): int(st.row_lo + st.local_rows)]))
+        ok_pr = ok_pr and ok
+        if rank == 0:
+            print(f"pagerank load={load} env={env} topics={n_t}: sweeps {st.sweeps} L1 {l1:.2e} "
+                  f"exposed exchange {st.exchange_ms_total / max(1, st.sweeps):.3f} ms/sweep, busy "
+                  f"{st.exchange_busy_ms_total / max(1, st.sweeps):.3f} -> {'ok' if ok else 'FAILED'}", flush=True)
+    for k in env:
+        del os.environ[k]
 rows = torch.tensor([st.local_rows, st.local_edges], dtype=torch.int64, device="cuda")
 allrows = [torch.zeros_like(rows) for _ in range(world)]
 dist.all_gather(allrows, rows)
 if rank == 0:
-    print("partition rows/edges:", [a.tolist() for a in allrows], "sweeps", st.sweeps, "L1", l1,
-          "exchange ms/sweep", st.exchange_ms_total / max(1, st.sweeps), flush=True)
+    print("partition rows/edges:", [a.tolist() for a in allrows], flush=True)
     assert sum(int(a[0]) for a in allrows) == N and sum(int(a[1]) for a in allrows) == int(row_ptr[-1])
 
 # ---- HP-2: doc-sharded index under shard-local doc ids, global df, cross-shard merge inside the engine

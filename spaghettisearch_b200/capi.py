@@ -20,7 +20,7 @@ SS_FLAG_TIMING = 1
 
 EXPORTS = [
     "ss_version", "ss_create", "ss_destroy", "ss_last_error", "ss_stream_handle", "ss_comm_unique_id", "ss_comm_init",
-    "ss_graph_load_csr", "ss_pagerank", "ss_pagerank_fetch", "ss_pagerank_get_stats", "ss_index_load",
+    "ss_graph_load_csr", "ss_graph_load_csr_rows", "ss_pagerank", "ss_pagerank_fetch", "ss_pagerank_set_teleport", "ss_pagerank_get_stats", "ss_index_load",
     "ss_index_clear", "ss_index_set_doc_base", "ss_score_batch_sharded",
     "ss_term_weights", "ss_set_doc_norms", "ss_set_pagerank", "ss_use_pagerank", "ss_score_batch",
     "ss_merge_topk", "ss_score_get_stats",
@@ -41,13 +41,14 @@ class PagerankStats(C.Structure):
     _fields_ = [("n_nodes", C.c_uint64), ("n_edges", C.c_uint64), ("row_lo", C.c_uint64), ("local_rows", C.c_uint64),
                 ("local_edges", C.c_uint64), ("sweeps", C.c_uint32), ("launches", C.c_uint32),
                 ("sweep_ms_total", C.c_double), ("gather_ms_total", C.c_double),
-                ("exchange_ms_total", C.c_double), ("load_ms", C.c_double), ("short_ms_total", C.c_double)]
+                ("exchange_ms_total", C.c_double), ("load_ms", C.c_double), ("short_ms_total", C.c_double),
+                ("exchange_busy_ms_total", C.c_double)]
 
 
 class ScoreStats(C.Structure):
     _fields_ = [("postings_scanned", C.c_uint64), ("docs_matched", C.c_uint64),
                 ("algorithmic_bytes", C.c_uint64), ("launches", C.c_uint32), ("kernel_ms", C.c_double),
-                ("score_kernel_ms", C.c_double), ("shard_merge_ms", C.c_double)]
+                ("score_kernel_ms", C.c_double), ("shard_merge_ms", C.c_double), ("model_bytes", C.c_uint64)]
 
 
 _lib = None
@@ -79,7 +80,9 @@ def load():
     L.ss_comm_unique_id.argtypes = [vp]
     L.ss_comm_init.argtypes = [vp, vp, i32, i32]
     L.ss_graph_load_csr.argtypes = [vp, u64, u64, vp, vp]
+    L.ss_graph_load_csr_rows.argtypes = [vp, u64, u64, u64, vp, vp]
     L.ss_pagerank.argtypes = [vp, dbl, dbl, u32, vp, u32, vp, vp]
+    L.ss_pagerank_set_teleport.argtypes = [vp, u64, u32, vp]
     L.ss_pagerank_fetch.argtypes = [vp, u64, u64, vp]
     L.ss_pagerank_get_stats.argtypes = [vp, C.POINTER(PagerankStats)]
     L.ss_index_load.argtypes = [vp, C.c_int, u64, u64, vp, vp, vp, vp, vp]
@@ -174,6 +177,12 @@ class Engine:
         self._check(self.L.ss_graph_load_csr(self.h, n, len(col_idx), _ptr(row_ptr), _ptr(col_idx)))
         self.n_nodes = n
 
+    def graph_load_csr_rows(self, n_nodes, row_lo, row_hi, row_ptr, col_idx):
+        """Sharded export: this rank's slice [row_lo, row_hi) of the CSR (row_ptr local to the slice)."""
+        row_ptr, col_idx = _as(row_ptr, np.uint64), _as(col_idx, np.uint32)
+        assert len(row_ptr) == row_hi - row_lo + 1
+        self._check(self.L.ss_graph_load_csr_rows(self.h, n_nodes, row_lo, row_hi, _ptr(row_ptr), _ptr(col_idx)))
+
     def pagerank(self, damping, eps, num_pages, max_iters=0, out=None, want_rank=True):
         """-> (rank [N][T] or None, iters [T], status)."""
         num_pages = np.ascontiguousarray(num_pages, dtype=np.int64)
@@ -185,6 +194,14 @@ class Engine:
                                             _ptr(iters)))
         self.n_topics = t
         return out, iters[:t], rc
+
+    def pagerank_set_teleport(self, weight):
+        """Topic-biased teleport (extension): weight [N][T] = N * v_t[v]; None resets to the reference's uniform."""
+        if weight is None:
+            self._check(self.L.ss_pagerank_set_teleport(self.h, 0, 0, None))
+            return
+        weight = _as(weight, np.float64)
+        self._check(self.L.ss_pagerank_set_teleport(self.h, weight.shape[0], weight.shape[1], _ptr(weight)))
 
     def pagerank_fetch(self, row_lo, row_hi, out=None):
         if out is None:

@@ -30,6 +30,8 @@ struct NcclApi {
   decltype(&ncclAllReduce) AllReduce = nullptr;
   decltype(&ncclBroadcast) Broadcast = nullptr;
   decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
   decltype(&ncclGroupStart) GroupStart = nullptr;
   decltype(&ncclGroupEnd) GroupEnd = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
@@ -52,6 +54,8 @@ static NcclApi* nccl_api() {
     SS_SYM(AllReduce);
     SS_SYM(Broadcast);
     SS_SYM(AllGather);
+    SS_SYM(Send);
+    SS_SYM(Recv);
     SS_SYM(GroupStart);
     SS_SYM(GroupEnd);
     SS_SYM(GetErrorString);
@@ -92,15 +96,22 @@ void comm_state_free(CommState* c) {
 int comm_rank(const ss_engine* e) { return e->comm ? e->comm->rank : 0; }
 int comm_world(const ss_engine* e) { return e->comm ? e->comm->world : 1; }
 
-int comm_allreduce_sum_f64(ss_engine* e, double* dev_buf, size_t count) {
+int comm_allreduce_sum_f64_on(ss_engine* e, cudaStream_t st, double* dev_buf, size_t count) {
   if (!e->comm || e->comm->world == 1) return SS_OK;
   auto* api = ss::nccl_api();
   SS_REQUIRE(api, SS_ERR_NCCL, "libnccl not loadable");
-  SS_NCCL(api, api->AllReduce(dev_buf, dev_buf, count, ncclDouble, ncclSum, e->comm->comm, e->stream));
+  SS_NCCL(api, api->AllReduce(dev_buf, dev_buf, count, ncclDouble, ncclSum, e->comm->comm, st));
   return SS_OK;
+}
+int comm_allreduce_sum_f64(ss_engine* e, double* dev_buf, size_t count) {
+  return comm_allreduce_sum_f64_on(e, e->stream, dev_buf, count);
 }
 
 int comm_allgatherv_bytes(ss_engine* e, void* dev_buf, const size_t* byte_off, const size_t* byte_cnt) {
+  return comm_allgatherv_bytes_on(e, e->stream, dev_buf, byte_off, byte_cnt);
+}
+int comm_allgatherv_bytes_on(ss_engine* e, cudaStream_t st, void* dev_buf, const size_t* byte_off,
+                             const size_t* byte_cnt) {
   if (!e->comm || e->comm->world == 1) return SS_OK;
   auto* api = ss::nccl_api();
   SS_REQUIRE(api, SS_ERR_NCCL, "libnccl not loadable");
@@ -109,10 +120,48 @@ int comm_allgatherv_bytes(ss_engine* e, void* dev_buf, const size_t* byte_off, c
   for (int r = 0; r < e->comm->world; ++r) {
     if (byte_cnt[r] == 0) continue;
     char* p = (char*)dev_buf + byte_off[r];
-    const ncclResult_t rc = api->Broadcast(p, p, byte_cnt[r], ncclChar, r, e->comm->comm, e->stream);
+    const ncclResult_t rc = api->Broadcast(p, p, byte_cnt[r], ncclChar, r, e->comm->comm, st);
     if (rc != ncclSuccess && first == ncclSuccess) first = rc;
   }
   const ncclResult_t end = api->GroupEnd();  // always closed, also on the error path
+  SS_NCCL(api, first);
+  SS_NCCL(api, end);
+  return SS_OK;
+}
+
+int comm_allreduce_sum_u32(ss_engine* e, uint32_t* dev_buf, size_t count) {
+  if (!e->comm || e->comm->world == 1) return SS_OK;
+  auto* api = ss::nccl_api();
+  SS_REQUIRE(api, SS_ERR_NCCL, "libnccl not loadable");
+  SS_NCCL(api, api->AllReduce(dev_buf, dev_buf, count, ncclUint32, ncclSum, e->comm->comm, e->stream));
+  return SS_OK;
+}
+
+int comm_alltoallv_u32(ss_engine* e, int n, const uint32_t* const* send, const size_t* send_off, const size_t* send_cnt,
+                       uint32_t* const* recv, const size_t* recv_off, const size_t* recv_cnt) {
+  const int world = comm_world(e), rank = comm_rank(e);
+  if (world == 1) {
+    for (int i = 0; i < n; ++i)
+      if (send_cnt[0])
+        SS_CUDA(cudaMemcpyAsync(recv[i] + recv_off[0], send[i] + send_off[0], send_cnt[0] * 4, cudaMemcpyDeviceToDevice,
+                                e->stream));
+    return SS_OK;
+  }
+  auto* api = ss::nccl_api();
+  SS_REQUIRE(api && api->Send && api->Recv, SS_ERR_NCCL, "libnccl not loadable (Send/Recv)");
+  (void)rank;
+  SS_NCCL(api, api->GroupStart());
+  ncclResult_t first = ncclSuccess;
+  for (int i = 0; i < n; ++i)
+    for (int r = 0; r < world; ++r) {
+      ncclResult_t rc = ncclSuccess;
+      if (send_cnt[r]) rc = api->Send(send[i] + send_off[r], send_cnt[r], ncclUint32, r, e->comm->comm, e->stream);
+      if (rc != ncclSuccess && first == ncclSuccess) first = rc;
+      rc = ncclSuccess;
+      if (recv_cnt[r]) rc = api->Recv(recv[i] + recv_off[r], recv_cnt[r], ncclUint32, r, e->comm->comm, e->stream);
+      if (rc != ncclSuccess && first == ncclSuccess) first = rc;
+    }
+  const ncclResult_t end = api->GroupEnd();
   SS_NCCL(api, first);
   SS_NCCL(api, end);
   return SS_OK;

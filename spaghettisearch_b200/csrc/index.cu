@@ -213,6 +213,8 @@ SS_API int ss_index_load(ss_engine* e, int table, uint64_t n_terms, uint64_t n_d
     ss::set_error("ss_index_load: pointers not monotone, doc id >= n_docs, or docs not ascending within a term");
     return SS_ERR_INVALID;
   }
+  tb.df_host.resize(V);
+  for (uint64_t t = 0; t < V; ++t) tb.df_host[t] = (uint32_t)(term_ptr[t + 1] - term_ptr[t]);
   tb.loaded = true;
   // everything derived from the doc id space, the weights or the norms is stale now
   ix->dense_valid = false;

@@ -14,8 +14,10 @@ struct TableState {
   ss::DevBuf<float> pos;          // listPos[1:]
   bool has_mag = false;
   ss::DevBuf<double> mag;         // [D] doc norms (forw[4])
+  std::vector<uint32_t> df_host;  // [V] postings per term, host copy (byte model of ss_score_stats)
   void clear() {
     loaded = has_pos = has_mag = false;
+    df_host.clear();
     V = P = 0;
     term_ptr.reset();
     doc_ids.reset();
@@ -55,6 +57,7 @@ struct IndexState {
   ss::DevBuf<float> zblk;       // [d_pad / 4096] largest blend term per doc block
   ss::DevBuf<uint8_t> dense_map;  // [V] dense slot of a term, 255 = none
   uint64_t dense_map_V = 0;
+  std::vector<uint8_t> dense_host;  // [dense_map_V] 1 = the term has an impact vector (host copy for the byte model)
   ss_score_stats stats{};
   // grow-only device workspace of ss_score_batch (cudaMalloc/cudaFree per batch would
   // synchronise the device and dominate small batches)

@@ -77,9 +77,11 @@ struct SweepParams {
   const uint32_t* warp_rows;  // [n_warps + 1] row range of every warp of the async short-row kernel
   const double* inv_tot;    // [TP] 1 / (S_t + (1-d) N)
   const double* init;       // [TP] 1/num_pages[t]
+  const double* tele_w;     // [rows_loc][TP] teleport weights N * v_t[v] of this rank's rows, or NULL = uniform
   double* red;              // [slots][3*TP] per-CTA partial sums (delta, S, changed)
   uint64_t row_lo;          // global id of local row 0
-  uint32_t rows_loc;
+  uint32_t row_begin;       // first local row of this launch's chunk (lean short-row kernel)
+  uint32_t rows_loc;        // one past the last local row of this launch's chunk
   uint32_t active_mask;     // bit t set: topic t still iterating
   double tele;              // 1 - d
   int first;                // sweep 1: add 1/n, compare against 1/n
@@ -178,6 +180,14 @@ __device__ __forceinline__ void epilogue(const SweepParams& p, uint32_t r, int l
   // five orders of magnitude inside the 1e-9 L1 budget.
   const double inv_mul = has_out ? 1.0 / m : 1.0;
   const Vec<VEC> inv_tot = ld_row_plain<VEC>(p.inv_tot + VEC * l8);
+  Vec<VEC> tw;  // teleport term per topic: (1-d), or (1-d) * N * v_t[v] for a topic-biased run
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) tw.v[j] = p.tele;
+  if (p.tele_w) {
+    const Vec<VEC> w = ld_row_stream<VEC>(p.tele_w + (uint64_t)r * TP + VEC * l8);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) tw.v[j] = __dmul_rn(p.tele, w.v[j]);
+  }
   Vec<VEC> yn;
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
@@ -189,7 +199,7 @@ __device__ __forceinline__ void epilogue(const SweepParams& p, uint32_t r, int l
       last_rank = i0;
     }
     if ((p.active_mask >> t) & 1u) {
-      const double nr = (a.v[j] + p.tele) * inv_tot.v[j];
+      const double nr = (a.v[j] + tw.v[j]) * inv_tot.v[j];
       acc.d[j] += fabs(nr - last_rank);
       yn.v[j] = nr * mul;
       acc.c[j] += (__double_as_longlong(yn.v[j]) != __double_as_longlong(yl.v[j])) ? 1.0 : 0.0;
@@ -347,6 +357,14 @@ __device__ __forceinline__ void epilogue2(const SweepParams& p, uint32_t r, int 
   const uint64_t v = p.row_lo + r;
   const bool has_out = m2.y > 0.0;
   const double mul = m2.x, inv_mul = fabs(m2.y);
+  Vec<VEC> tw;  // see epilogue()
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) tw.v[j] = p.tele;
+  if (p.tele_w) {
+    const Vec<VEC> w = ld_row_stream<VEC>(p.tele_w + (uint64_t)r * TP + VEC * l8);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) tw.v[j] = __dmul_rn(p.tele, w.v[j]);
+  }
   Vec<VEC> yn;
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
@@ -355,7 +373,7 @@ __device__ __forceinline__ void epilogue2(const SweepParams& p, uint32_t r, int 
       a.v[j] += init.v[j];
       last_rank = init.v[j];
     }
-    const double nr = (a.v[j] + p.tele) * inv_tot.v[j];
+    const double nr = (a.v[j] + tw.v[j]) * inv_tot.v[j];
     const double cand = nr * mul;
     const bool live = ALL || ((p.active_mask >> (VEC * l8 + j)) & 1u);
     if (live) {
@@ -397,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_sweep_short32(SweepParams p, ui
 #pragma unroll
   for (int c = 0; c < VEC; ++c) init.v[c] = FIRST ? p.init[VEC * l8 + c] : 0.0;
   const uint32_t step = gridDim.x * GPC;
-  uint32_t r = blockIdx.x * GPC + group_in_cta;
+  uint32_t r = p.row_begin + blockIdx.x * GPC + group_in_cta;
   // the pointer array is padded past rows_loc by three grid strides (ss_graph_load_csr)
   uint32_t b_c = ptr[r], e_c = ptr[r + 1];
   uint32_t b_n = ptr[r + step], e_n = ptr[r + step + 1];
@@ -814,6 +832,15 @@ __global__ void __launch_bounds__(kThreads) k_init(double* __restrict__ y, const
   }
 }
 
+// teleport weights [rows][T] -> [rows][TP] (padded columns get 1: they are frozen anyway)
+__global__ void k_pad_rows(const double* __restrict__ in, uint64_t rows, int T, int TP, double* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * (uint64_t)TP) return;
+  const uint64_t r = i / TP;
+  const int t = (int)(i % TP);
+  out[i] = t < T ? in[r * T + t] : 1.0;
+}
+
 // rank[v][t] = y[v][t] / m(v) for rows [lo, hi) into a dense [rows][T] buffer.
 __global__ void k_unscale(const double* __restrict__ y, const uint32_t* __restrict__ outdeg, double damping,
                           int TP, int T, uint64_t lo, uint64_t hi, double* __restrict__ out) {
@@ -836,7 +863,7 @@ __global__ void k_outdeg(const uint64_t* __restrict__ row_ptr, uint64_t n, uint3
 // binary search, then a walk over the row boundaries); children validated.
 __global__ void k_expand_src4(const uint64_t* __restrict__ row_ptr, uint64_t n, uint64_t n_edges,
                               const uint32_t* __restrict__ col_idx, uint32_t* __restrict__ src,
-                              int* __restrict__ bad) {
+                              int* __restrict__ bad, uint64_t n_child) {
   const uint64_t e0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (e0 >= n_edges) return;
   uint64_t lo = 0, hi = n;  // last u with row_ptr[u] <= e0
@@ -849,8 +876,21 @@ __global__ void k_expand_src4(const uint64_t* __restrict__ row_ptr, uint64_t n, 
   for (uint64_t e = e0; e < e1; ++e) {
     while (e >= next) next = row_ptr[++u + 1];
     src[e] = (uint32_t)u;
-    if (col_idx[e] >= n) *bad = 1;
+    if (col_idx[e] >= n_child) *bad = 1;
   }
+}
+// sharded load: cnt[v] = in-edges of v inside this rank's slice, from the slice's child-sorted list
+__global__ void k_count_from_ptr(const unsigned long long* __restrict__ ptr, uint64_t n, uint32_t* __restrict__ cnt) {
+  const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) cnt[v] = (uint32_t)(ptr[v + 1] - ptr[v]);
+}
+__global__ void k_widen_counts(const uint32_t* __restrict__ cnt, uint64_t n, unsigned long long* __restrict__ out) {
+  const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v <= n) out[v] = v < n ? cnt[v] : 0ull;
+}
+__global__ void k_add_u32(uint32_t* __restrict__ a, uint64_t n, uint32_t add) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += add;
 }
 // in_ptr[v] = first position of child v in the child-sorted edge list
 __global__ void k_in_ptr_from_sorted(const uint32_t* __restrict__ dst_sorted, uint64_t n_edges, uint64_t n,
@@ -863,6 +903,19 @@ __global__ void k_in_ptr_from_sorted(const uint32_t* __restrict__ dst_sorted, ui
     if (dst_sorted[mid] < v) lo = mid + 1; else hi = mid;
   }
   in_ptr[v] = lo;
+}
+// sharded load: in_ptr_loc[i] = first position of child row_lo + i in this rank's child-sorted in-edge list
+__global__ void k_in_ptr_local(const uint32_t* __restrict__ dst_sorted, uint64_t n_edges, uint64_t row_lo,
+                               uint32_t rows_loc, uint64_t* __restrict__ in_ptr_loc) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > rows_loc) return;
+  const uint64_t v = row_lo + i;
+  uint64_t lo = 0, hi = n_edges;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (dst_sorted[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  in_ptr_loc[i] = lo;
 }
 __global__ void k_check_row_ptr(const uint64_t* __restrict__ row_ptr, uint64_t n, uint64_t n_edges,
                                 int* __restrict__ bad) {
@@ -956,11 +1009,14 @@ __global__ void k_count_tasks(const uint64_t* __restrict__ in_ptr, uint32_t rows
 __global__ void k_fill_tasks(const uint64_t* __restrict__ in_ptr, const uint32_t* __restrict__ in_src,
                              uint32_t rows_loc, const uint32_t* __restrict__ nt, const uint32_t* __restrict__ toff,
                              const uint32_t* __restrict__ foff, LongTask* __restrict__ tasks,
-                             uint32_t* __restrict__ keys, uint32_t* __restrict__ order, FixRow* __restrict__ fix) {
+                             unsigned long long* __restrict__ keys, uint32_t* __restrict__ order,
+                             FixRow* __restrict__ fix, const unsigned long long* __restrict__ chunk_rows, int n_chunks) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows_loc) return;
   const uint32_t t = nt[r];
   if (t == 0) return;
+  unsigned long long chunk = 0;  // row chunk of the overlapped exchange (0 when there is one chunk)
+  while ((int)chunk + 1 < n_chunks && r >= chunk_rows[chunk + 1]) ++chunk;
   const uint64_t b = in_ptr[r], deg = in_ptr[r + 1] - b;
   const uint32_t base = toff[r];
   for (uint32_t c = 0; c < t; ++c) {
@@ -971,7 +1027,7 @@ __global__ void k_fill_tasks(const uint64_t* __restrict__ in_ptr, const uint32_t
     k.slot = t > 1 ? (int32_t)(base + c) : -1;
     k.pad = 0;
     tasks[base + c] = k;
-    keys[base + c] = in_src[k.e_begin];
+    keys[base + c] = (chunk << 32) | in_src[k.e_begin];  // grouped by chunk, then by first source
     order[base + c] = base + c;
   }
   if (t > 1) {
@@ -1010,6 +1066,15 @@ struct PagerankState {
   ss::DevBuf<LongTask> tasks;
   ss::DevBuf<FixRow> fix;
   uint32_t n_tasks = 0, n_fix = 0;
+  // Row chunks of the overlapped exchange (> 2 ranks over NCCL): the rank's rows are cut into n_chunks
+  // edge-balanced ranges; a sweep finishes chunk c (short rows, long-row tasks, fix rows) and broadcasts
+  // it on the exchange stream while chunk c + 1 computes.  One chunk otherwise.
+  int n_chunks = 1;
+  std::vector<uint32_t> chunk_rows, chunk_task, chunk_fix;  // [n_chunks + 1] local row / task / fix-row boundaries
+  std::vector<uint64_t> all_chunk_rows;                     // [world][n_chunks + 1] global row boundaries of every rank
+  cudaStream_t xstream = nullptr;                           // exchange stream (NCCL calls of the sweep loop)
+  cudaEvent_t chunk_ev[8] = {}, x_done = nullptr, red_done = nullptr;
+  cudaEvent_t x_t0 = nullptr, x_t1 = nullptr;               // timing: exchange stream busy interval of a sweep
   // per-run state
   int TP = 0, T = 0;
   double damping = 0;
@@ -1017,6 +1082,9 @@ struct PagerankState {
   int cur = 0;  // y[cur] holds the latest ranks
   ss::DevBuf<double> mul, partials, red, stage, sums, tot, init, out_stage[2];
   bool have_result = false;
+  // topic-biased teleport (ss_pagerank_set_teleport): weights of this rank's rows, [rows_loc][tele_T] as given
+  ss::DevBuf<double> tele_raw, tele_w;  // raw [rows_loc][tele_T]; padded [rows_loc][TP] built per run
+  uint32_t tele_T = 0;                  // 0: uniform teleport (the reference)
   ss_pagerank_stats stats{};
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [4]: end of the short-row kernel
   cudaEvent_t out_ev[2] = {nullptr, nullptr};
@@ -1028,8 +1096,9 @@ struct PagerankState {
   // load-time scratch, kept between loads (grow-only)
   struct Scratch {
     ss::DevBuf<uint64_t> row_ptr;
-    ss::DevBuf<uint32_t> col, src, col_sorted, src_sorted, nt, nf, toff, foff, keys, keys_out, order, order_out, sdeg;
-    ss::DevBuf<unsigned long long> in_ptr_full, bounds;
+    ss::DevBuf<uint32_t> col, src, col_sorted, src_sorted, nt, nf, toff, foff, order, order_out, sdeg;
+    ss::DevBuf<unsigned long long> in_ptr_full, bounds, keys, keys_out, chunk_rows, slice_ptr;
+    ss::DevBuf<uint32_t> cnt, recv_col, recv_src;
     ss::DevBuf<int> bad;
     ss::DevBuf<char> tmp;
     ss::DevBuf<LongTask> unsorted;
@@ -1116,6 +1185,13 @@ void pagerank_state_free(PagerankState* s) {
     if (e) cudaEventDestroy(e);
   for (auto& e : s->out_ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : s->chunk_ev)
+    if (e) cudaEventDestroy(e);
+  if (s->x_done) cudaEventDestroy(s->x_done);
+  if (s->red_done) cudaEventDestroy(s->red_done);
+  if (s->x_t0) cudaEventDestroy(s->x_t0);
+  if (s->x_t1) cudaEventDestroy(s->x_t1);
+  if (s->xstream) cudaStreamDestroy(s->xstream);
   delete s;
 }
 
@@ -1150,6 +1226,167 @@ static int dispatch_shape(Shape sh, F&& f) {
   return f(integral_constant<int, 4>(), integral_constant<int, 4>());
 }
 
+static int create_sync_objects(PagerankState* s) {
+  for (auto& ev : s->ev) SS_CUDA(cudaEventCreate(&ev));
+  for (auto& ev : s->out_ev) SS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto& ev : s->chunk_ev) SS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  SS_CUDA(cudaEventCreateWithFlags(&s->x_done, cudaEventDisableTiming));
+  SS_CUDA(cudaEventCreateWithFlags(&s->red_done, cudaEventDisableTiming));
+  SS_CUDA(cudaEventCreate(&s->x_t0));
+  SS_CUDA(cudaEventCreate(&s->x_t1));
+  SS_CUDA(cudaStreamCreateWithFlags(&s->xstream, cudaStreamNonBlocking));
+  return SS_OK;
+}
+
+// Second half of a graph load, shared by ss_graph_load_csr and ss_graph_load_csr_rows: everything that only
+// depends on this rank's in-edge lists (s->in_ptr, s->in_src), the global out-degrees and the partition.
+static int finish_load(ss_engine* e, PagerankState* s, std::chrono::steady_clock::time_point t_begin) {
+  PagerankState::Scratch& sc = s->sc;
+  cudaStream_t st = e->stream;
+  const uint64_t N = s->N, E = s->E;
+  const int world = comm_world(e);
+  s->ptr32_pad = 0;
+  if (s->E_loc < 0xFFFFFFFFull) {
+    // padding: GPC <= 256 rows per CTA and step, persistent grid <= 8 CTAs per SM, two strides ahead
+    const uint64_t pad = 2ull * (uint64_t)e->sm_count * 8 * 256 + 1024;
+    const uint64_t n_padded = (uint64_t)s->rows_loc + 1 + pad;
+    SS_TRY(s->in_ptr32.reserve(n_padded));
+    k_local_ptr32<<<ss::div_up(n_padded, 256), 256, 0, st>>>(s->in_ptr.p, s->rows_loc, n_padded, s->in_ptr32.p);
+    s->ptr32_pad = pad;
+  }
+
+  // short-only CSR of the cp.async ring kernel: measured equal to the lean register kernel at
+  // configs[1] (1.39 vs 1.38 ms: both sit at the chip's random 128-byte row rate), so it is opt-in
+  // and its structures are only built on request
+  s->have_short = false;
+  const char* short_env = getenv("SS_PR_SHORT");
+  if (short_env && !strcmp(short_env, "async") && s->E_loc < 0xFFFFFFFFull && s->rows_loc) {
+    const uint32_t R = s->rows_loc, pad = 64;
+    SS_TRY(sc.sdeg.reserve((size_t)R + 1));
+    SS_TRY(s->sptr.reserve((size_t)R + 2 + pad));
+    k_short_deg<<<ss::div_up((uint64_t)R + 1, 256), 256, 0, st>>>(s->in_ptr.p, R, sc.sdeg.p);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, sc.sdeg.p, s->sptr.p, (int)(R + 1), st);
+    SS_TRY(sc.tmp.reserve(tmp_bytes));
+    tmp_bytes = sc.tmp.n;
+    SS_CUDA(cub::DeviceScan::ExclusiveSum(sc.tmp.p, tmp_bytes, sc.sdeg.p, s->sptr.p, (int)(R + 1), st));
+    uint32_t e_short = 0;
+    SS_CUDA(cudaMemcpyAsync(&e_short, s->sptr.p + R, 4, cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaStreamSynchronize(st));
+    s->E_short = e_short;
+    SS_TRY(s->ssrc.reserve((size_t)e_short + 64));
+    k_short_compact<<<ss::div_up((uint64_t)R + pad, 256), 256, 0, st>>>(s->in_ptr.p, s->in_src.p, s->sptr.p, R, pad,
+                                                                       s->sptr.p, s->ssrc.p);
+    s->have_short = true;
+  }
+
+  // row chunks of the overlapped exchange
+  {
+    int C = world > 2 ? 4 : 1;
+    if (const char* env = getenv("SS_PR_CHUNKS")) C = std::max(1, std::min(8, atoi(env)));
+    if (world == 1 || s->rows_loc < 4096u * C || s->ptr32_pad == 0) C = 1;
+    if (world > 1) {  // every rank must cut its block into the same number of chunks
+      int32_t mine = C, all[64];
+      SS_TRY(comm_allgather_host_bytes(e, &mine, sizeof(mine), all));
+      for (int r = 0; r < world; ++r) C = std::min<int>(C, all[r]);
+    }
+    s->n_chunks = C;
+    SS_TRY(sc.chunk_rows.reserve(C + 1));
+    std::vector<unsigned long long> hc(C + 1, 0);
+    hc[C] = s->rows_loc;
+    if (C > 1) {
+      k_partition<<<1, 64, 0, st>>>(reinterpret_cast<const unsigned long long*>(s->in_ptr.p), s->rows_loc, C,
+                                    sc.chunk_rows.p);
+      SS_CUDA(cudaMemcpyAsync(hc.data(), sc.chunk_rows.p, (C + 1) * 8, cudaMemcpyDeviceToHost, st));
+      SS_CUDA(cudaStreamSynchronize(st));
+    } else {
+      SS_CUDA(cudaMemcpyAsync(sc.chunk_rows.p, hc.data(), (C + 1) * 8, cudaMemcpyHostToDevice, st));
+      SS_CUDA(cudaStreamSynchronize(st));
+    }
+    s->chunk_rows.assign(hc.begin(), hc.end());
+    s->chunk_task.assign(C + 1, 0);
+    s->chunk_fix.assign(C + 1, 0);
+  }
+
+  // long-row tasks and fix rows
+  s->n_tasks = s->n_fix = 0;
+  if (s->rows_loc) {
+    const uint32_t R = s->rows_loc;
+    SS_TRY(sc.nt.reserve((size_t)R + 1));
+    SS_TRY(sc.nf.reserve((size_t)R + 1));
+    SS_TRY(sc.toff.reserve((size_t)R + 1));
+    SS_TRY(sc.foff.reserve((size_t)R + 1));
+    SS_CUDA(cudaMemsetAsync(sc.nt.p + R, 0, 4, st));
+    SS_CUDA(cudaMemsetAsync(sc.nf.p + R, 0, 4, st));
+    k_count_tasks<<<ss::div_up(R, 256), 256, 0, st>>>(s->in_ptr.p, R, sc.nt.p, sc.nf.p);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, sc.nt.p, sc.toff.p, (int)(R + 1), st);
+    SS_TRY(sc.tmp.reserve(tmp_bytes));
+    tmp_bytes = sc.tmp.n;
+    SS_CUDA(cub::DeviceScan::ExclusiveSum(sc.tmp.p, tmp_bytes, sc.nt.p, sc.toff.p, (int)(R + 1), st));
+    tmp_bytes = sc.tmp.n;
+    SS_CUDA(cub::DeviceScan::ExclusiveSum(sc.tmp.p, tmp_bytes, sc.nf.p, sc.foff.p, (int)(R + 1), st));
+    uint32_t n_tasks = 0, n_fix = 0;
+    SS_CUDA(cudaMemcpyAsync(&n_tasks, sc.toff.p + R, 4, cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaMemcpyAsync(&n_fix, sc.foff.p + R, 4, cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaStreamSynchronize(st));
+    s->n_tasks = n_tasks;
+    s->n_fix = n_fix;
+    for (int c = 0; c <= s->n_chunks; ++c) {  // task / fix-row boundaries of the chunks (scans are in row order)
+      SS_CUDA(cudaMemcpyAsync(&s->chunk_task[c], sc.toff.p + s->chunk_rows[c], 4, cudaMemcpyDeviceToHost, st));
+      SS_CUDA(cudaMemcpyAsync(&s->chunk_fix[c], sc.foff.p + s->chunk_rows[c], 4, cudaMemcpyDeviceToHost, st));
+    }
+    SS_CUDA(cudaStreamSynchronize(st));
+    if (n_tasks) {
+      SS_TRY(sc.unsorted.reserve(n_tasks));
+      SS_TRY(s->tasks.reserve(n_tasks));
+      SS_TRY(s->fix.reserve(n_fix));
+      SS_TRY(sc.keys.reserve(n_tasks));
+      SS_TRY(sc.keys_out.reserve(n_tasks));
+      SS_TRY(sc.order.reserve(n_tasks));
+      SS_TRY(sc.order_out.reserve(n_tasks));
+      k_fill_tasks<<<ss::div_up(R, 256), 256, 0, st>>>(s->in_ptr.p, s->in_src.p, R, sc.nt.p, sc.toff.p, sc.foff.p,
+                                                       sc.unsorted.p, sc.keys.p, sc.order.p, s->fix.p,
+                                                       sc.chunk_rows.p, s->n_chunks);
+      size_t sort_bytes = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, sc.keys.p, sc.keys_out.p, sc.order.p, sc.order_out.p,
+                                      (int)n_tasks, 0, 36, st);
+      SS_TRY(sc.tmp.reserve(sort_bytes));
+      sort_bytes = sc.tmp.n;
+      SS_CUDA(cub::DeviceRadixSort::SortPairs(sc.tmp.p, sort_bytes, sc.keys.p, sc.keys_out.p, sc.order.p,
+                                              sc.order_out.p, (int)n_tasks, 0, 36, st));
+      k_gather_tasks<<<ss::div_up(n_tasks, 256), 256, 0, st>>>(sc.unsorted.p, sc.order_out.p, n_tasks, s->tasks.p);
+    }
+  }
+  SS_CUDA(cudaStreamSynchronize(st));
+  SS_CUDA(cudaGetLastError());
+  s->tele_T = 0;  // teleport weights belong to the previous partition
+  s->stats = ss_pagerank_stats{};
+  s->stats.n_nodes = N;
+  s->stats.n_edges = E;
+  s->stats.row_lo = s->row_lo;
+  s->stats.local_rows = s->rows_loc;
+  s->stats.local_edges = s->E_loc;
+  s->stats.load_ms =
+      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  s->loaded = true;
+  return SS_OK;
+}
+
+// rank rows [lo, hi) of the last result -> host.  The idle state buffer y[cur ^ 1] is the staging area.
+static int unscale_and_copy(ss_engine* e, PagerankState* s, uint64_t lo, uint64_t hi, double* out_rank) {
+  if (hi <= lo || s->T == 0) return SS_OK;
+  cudaStream_t st = e->stream;
+  const uint64_t total = (hi - lo) * (uint64_t)s->T;
+  double* stage = s->y[s->cur ^ 1].p;
+  k_unscale<<<ss::div_up(total, 256), 256, 0, st>>>(s->y[s->cur].p, s->outdeg.p, s->damping, s->TP, s->T, lo, hi, stage);
+  SS_CUDA(cudaMemcpyAsync(out_rank, stage, total * 8, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaStreamSynchronize(st));
+  SS_CUDA(cudaGetLastError());
+  s->stats.launches += 1;
+  return SS_OK;
+}
+
 extern "C" {
 
 SS_API int ss_graph_load_csr(ss_engine* e, uint64_t n_nodes, uint64_t n_edges, const uint64_t* row_ptr,
@@ -1163,8 +1400,7 @@ SS_API int ss_graph_load_csr(ss_engine* e, uint64_t n_nodes, uint64_t n_edges, c
   if (!e->pr) {
     e->pr = new (std::nothrow) PagerankState();
     SS_REQUIRE(e->pr, SS_ERR_OOM, "host allocation failed");
-    for (auto& ev : e->pr->ev) SS_CUDA(cudaEventCreate(&ev));
-    for (auto& ev : e->pr->out_ev) SS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    SS_TRY(create_sync_objects(e->pr));
   }
   PagerankState* s = e->pr;  // device blocks are reused across loads
   PagerankState::Scratch& sc = s->sc;
@@ -1199,7 +1435,7 @@ SS_API int ss_graph_load_csr(ss_engine* e, uint64_t n_nodes, uint64_t n_edges, c
   SS_CUDA(cudaMemcpyAsync(&bad, sc.bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaStreamSynchronize(st));
   SS_REQUIRE(!bad, SS_ERR_INVALID, "ss_graph_load_csr: row_ptr not monotone or row_ptr[n] != n_edges");
-  if (E) k_expand_src4<<<ss::div_up(ss::div_up(E, 4), 256), 256, 0, st>>>(sc.row_ptr.p, N, E, sc.col.p, sc.src.p, sc.bad.p);
+  if (E) k_expand_src4<<<ss::div_up(ss::div_up(E, 4), 256), 256, 0, st>>>(sc.row_ptr.p, N, E, sc.col.p, sc.src.p, sc.bad.p, N);
   SS_CUDA(cudaMemcpyAsync(&bad, sc.bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
 
   // sort edges by child (stable: parents stay ascending inside a row)
@@ -1236,97 +1472,192 @@ SS_API int ss_graph_load_csr(ss_engine* e, uint64_t n_nodes, uint64_t n_edges, c
   k_local_ptr<<<ss::div_up((uint64_t)s->rows_loc + 1, 256), 256, 0, st>>>(sc.in_ptr_full.p, s->row_lo, s->rows_loc,
                                                                          s->in_ptr.p);
 
-  s->ptr32_pad = 0;
-  if (s->E_loc < 0xFFFFFFFFull) {
-    // padding: GPC <= 256 rows per CTA and step, persistent grid <= 8 CTAs per SM, two strides ahead
-    const uint64_t pad = 2ull * (uint64_t)e->sm_count * 8 * 256 + 1024;
-    const uint64_t n_padded = (uint64_t)s->rows_loc + 1 + pad;
-    SS_TRY(s->in_ptr32.reserve(n_padded));
-    k_local_ptr32<<<ss::div_up(n_padded, 256), 256, 0, st>>>(s->in_ptr.p, s->rows_loc, n_padded, s->in_ptr32.p);
-    s->ptr32_pad = pad;
-  }
+  return finish_load(e, s, t_begin);
+}
 
-  // short-only CSR of the cp.async ring kernel: measured equal to the lean register kernel at
-  // configs[1] (1.39 vs 1.38 ms: both sit at the chip's random 128-byte row rate), so it is opt-in
-  // and its structures are only built on request
-  s->have_short = false;
-  const char* short_env = getenv("SS_PR_SHORT");
-  if (short_env && !strcmp(short_env, "async") && s->E_loc < 0xFFFFFFFFull && s->rows_loc) {
-    const uint32_t R = s->rows_loc, pad = 64;
-    SS_TRY(sc.sdeg.reserve((size_t)R + 1));
-    SS_TRY(s->sptr.reserve((size_t)R + 2 + pad));
-    k_short_deg<<<ss::div_up((uint64_t)R + 1, 256), 256, 0, st>>>(s->in_ptr.p, R, sc.sdeg.p);
-    size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, sc.sdeg.p, s->sptr.p, (int)(R + 1), st);
-    SS_TRY(sc.tmp.reserve(tmp_bytes));
-    tmp_bytes = sc.tmp.n;
-    SS_CUDA(cub::DeviceScan::ExclusiveSum(sc.tmp.p, tmp_bytes, sc.sdeg.p, s->sptr.p, (int)(R + 1), st));
-    uint32_t e_short = 0;
-    SS_CUDA(cudaMemcpyAsync(&e_short, s->sptr.p + R, 4, cudaMemcpyDeviceToHost, st));
-    SS_CUDA(cudaStreamSynchronize(st));
-    s->E_short = e_short;
-    SS_TRY(s->ssrc.reserve((size_t)e_short + 64));
-    k_short_compact<<<ss::div_up((uint64_t)R + pad, 256), 256, 0, st>>>(s->in_ptr.p, s->in_src.p, s->sptr.p, R, pad,
-                                                                       s->sptr.p, s->ssrc.p);
-    s->have_short = true;
+/* Sharded export: every rank passes the slice [row_lo, row_hi) of the out-edge CSR it exported (spaghetti.h).
+ * Each slice is sorted by child on its own GPU, in-degrees are summed over the ranks, the partition is cut,
+ * and every rank receives exactly the in-edges of the rows it owns (one all-to-all over NVLink): H2D bytes,
+ * sort work and scratch memory per rank are 1/world of the replicated load. */
+SS_API int ss_graph_load_csr_rows(ss_engine* e, uint64_t n_nodes, uint64_t row_lo, uint64_t row_hi,
+                                  const uint64_t* row_ptr, const uint32_t* col_idx) {
+  SS_REQUIRE(e, SS_ERR_INVALID, "ss_graph_load_csr_rows: engine is NULL");
+  SS_REQUIRE(row_ptr && row_lo <= row_hi && row_hi <= n_nodes, SS_ERR_INVALID, "ss_graph_load_csr_rows: bad slice");
+  SS_REQUIRE(n_nodes < 0xFFFFFFFFull, SS_ERR_INVALID, "ss_graph_load_csr_rows: node ids are 32 bit");
+  SS_REQUIRE(row_ptr[0] == 0, SS_ERR_INVALID, "ss_graph_load_csr_rows: row_ptr is local to the slice (starts at 0)");
+  const uint64_t n_slice = row_hi - row_lo, E_slice = row_ptr[n_slice];
+  SS_REQUIRE(col_idx || E_slice == 0, SS_ERR_INVALID, "ss_graph_load_csr_rows: col_idx is NULL");
+  SS_REQUIRE(E_slice < 0xFFFFFFFFull, SS_ERR_INVALID, "ss_graph_load_csr_rows: slice has >= 2^32 edges");
+  if (comm_world(e) == 1) {
+    SS_REQUIRE(row_lo == 0 && row_hi == n_nodes, SS_ERR_INVALID,
+               "ss_graph_load_csr_rows: a single rank must pass every row");
+    return ss_graph_load_csr(e, n_nodes, E_slice, row_ptr, col_idx);
   }
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  auto t_begin = std::chrono::steady_clock::now();
+  if (!e->pr) {
+    e->pr = new (std::nothrow) PagerankState();
+    SS_REQUIRE(e->pr, SS_ERR_OOM, "host allocation failed");
+    SS_TRY(create_sync_objects(e->pr));
+  }
+  PagerankState* s = e->pr;
+  PagerankState::Scratch& sc = s->sc;
+  s->loaded = false;
+  s->have_result = false;
+  cudaStream_t st = e->stream;
+  const uint64_t N = n_nodes;
+  const int world = comm_world(e), rank = comm_rank(e);
+  SS_REQUIRE(world < 64, SS_ERR_INVALID, "world size %d too large", world);
+  s->N = N;
+  s->bounds.assign(world + 1, 0);
 
-  // long-row tasks and fix rows
-  s->n_tasks = s->n_fix = 0;
-  if (s->rows_loc) {
-    const uint32_t R = s->rows_loc;
-    SS_TRY(sc.nt.reserve((size_t)R + 1));
-    SS_TRY(sc.nf.reserve((size_t)R + 1));
-    SS_TRY(sc.toff.reserve((size_t)R + 1));
-    SS_TRY(sc.foff.reserve((size_t)R + 1));
-    SS_CUDA(cudaMemsetAsync(sc.nt.p + R, 0, 4, st));
-    SS_CUDA(cudaMemsetAsync(sc.nf.p + R, 0, 4, st));
-    k_count_tasks<<<ss::div_up(R, 256), 256, 0, st>>>(s->in_ptr.p, R, sc.nt.p, sc.nf.p);
-    size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, sc.nt.p, sc.toff.p, (int)(R + 1), st);
-    SS_TRY(sc.tmp.reserve(tmp_bytes));
-    tmp_bytes = sc.tmp.n;
-    SS_CUDA(cub::DeviceScan::ExclusiveSum(sc.tmp.p, tmp_bytes, sc.nt.p, sc.toff.p, (int)(R + 1), st));
-    tmp_bytes = sc.tmp.n;
-    SS_CUDA(cub::DeviceScan::ExclusiveSum(sc.tmp.p, tmp_bytes, sc.nf.p, sc.foff.p, (int)(R + 1), st));
-    uint32_t n_tasks = 0, n_fix = 0;
-    SS_CUDA(cudaMemcpyAsync(&n_tasks, sc.toff.p + R, 4, cudaMemcpyDeviceToHost, st));
-    SS_CUDA(cudaMemcpyAsync(&n_fix, sc.foff.p + R, 4, cudaMemcpyDeviceToHost, st));
-    SS_CUDA(cudaStreamSynchronize(st));
-    s->n_tasks = n_tasks;
-    s->n_fix = n_fix;
-    if (n_tasks) {
-      SS_TRY(sc.unsorted.reserve(n_tasks));
-      SS_TRY(s->tasks.reserve(n_tasks));
-      SS_TRY(s->fix.reserve(n_fix));
-      SS_TRY(sc.keys.reserve(n_tasks));
-      SS_TRY(sc.keys_out.reserve(n_tasks));
-      SS_TRY(sc.order.reserve(n_tasks));
-      SS_TRY(sc.order_out.reserve(n_tasks));
-      k_fill_tasks<<<ss::div_up(R, 256), 256, 0, st>>>(s->in_ptr.p, s->in_src.p, R, sc.nt.p, sc.toff.p, sc.foff.p,
-                                                       sc.unsorted.p, sc.keys.p, sc.order.p, s->fix.p);
-      size_t sort_bytes = 0;
-      cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, sc.keys.p, sc.keys_out.p, sc.order.p, sc.order_out.p,
-                                      (int)n_tasks, 0, 32, st);
-      SS_TRY(sc.tmp.reserve(sort_bytes));
-      sort_bytes = sc.tmp.n;
-      SS_CUDA(cub::DeviceRadixSort::SortPairs(sc.tmp.p, sort_bytes, sc.keys.p, sc.keys_out.p, sc.order.p,
-                                              sc.order_out.p, (int)n_tasks, 0, 32, st));
-      k_gather_tasks<<<ss::div_up(n_tasks, 256), 256, 0, st>>>(sc.unsorted.p, sc.order_out.p, n_tasks, s->tasks.p);
+  // Local phase: no collective in here.  Its status is agreed on below, so that a rank with a bad slice
+  // or no memory makes every rank return instead of leaving the others inside a collective.
+  int end_bit = 1;
+  while ((1ull << end_bit) < N) ++end_bit;
+  auto local_phase = [&]() -> int {
+    SS_TRY(sc.row_ptr.reserve(n_slice + 1));
+    SS_TRY(sc.col.reserve(E_slice));
+    SS_TRY(sc.src.reserve(E_slice));
+    SS_TRY(sc.col_sorted.reserve(E_slice));
+    SS_TRY(sc.src_sorted.reserve(E_slice));
+    SS_TRY(sc.slice_ptr.reserve(N + 2));
+    SS_TRY(sc.cnt.reserve(N + 1));
+    SS_TRY(sc.keys.reserve(N + 2));
+    SS_TRY(sc.in_ptr_full.reserve(N + 2));
+    SS_TRY(sc.bounds.reserve(world + 1));
+    SS_TRY(sc.bad.reserve(1));
+    SS_TRY(s->outdeg.reserve(N));
+    size_t tmp_bytes = 0, scan_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, sc.col.p, sc.col_sorted.p, sc.src.p, sc.src_sorted.p,
+                                    (int64_t)std::max<uint64_t>(E_slice, 1), 0, end_bit, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, sc.keys.p, sc.in_ptr_full.p, (int64_t)(N + 1), st);
+    SS_TRY(sc.tmp.reserve(std::max(tmp_bytes, scan_bytes)));
+    SS_CUDA(cudaMemcpyAsync(sc.row_ptr.p, row_ptr, (n_slice + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (E_slice) SS_CUDA(cudaMemcpyAsync(sc.col.p, col_idx, E_slice * 4, cudaMemcpyHostToDevice, st));
+    SS_CUDA(cudaMemsetAsync(sc.bad.p, 0, sizeof(int), st));
+    if (n_slice) {
+      k_check_row_ptr<<<ss::div_up(n_slice, 256), 256, 0, st>>>(sc.row_ptr.p, n_slice, E_slice, sc.bad.p);
+      k_outdeg<<<ss::div_up(n_slice, 256), 256, 0, st>>>(sc.row_ptr.p, n_slice, s->outdeg.p + row_lo);
     }
+    if (E_slice) {
+      k_expand_src4<<<ss::div_up(ss::div_up(E_slice, 4), 256), 256, 0, st>>>(sc.row_ptr.p, n_slice, E_slice, sc.col.p,
+                                                                            sc.src.p, sc.bad.p, N);
+      if (row_lo) k_add_u32<<<ss::div_up(E_slice, 256), 256, 0, st>>>(sc.src.p, E_slice, (uint32_t)row_lo);
+      tmp_bytes = sc.tmp.n;
+      SS_CUDA(cub::DeviceRadixSort::SortPairs(sc.tmp.p, tmp_bytes, sc.col.p, sc.col_sorted.p, sc.src.p,
+                                              sc.src_sorted.p, (int64_t)E_slice, 0, end_bit, st));
+    }
+    // slice_ptr[v] = first position of child v in the slice's sorted list; cnt[v] = its in-edges from this slice
+    k_in_ptr_from_sorted<<<ss::div_up(N + 1, 256), 256, 0, st>>>(sc.col_sorted.p, E_slice, N, sc.slice_ptr.p);
+    if (N) k_count_from_ptr<<<ss::div_up(N, 256), 256, 0, st>>>(sc.slice_ptr.p, N, sc.cnt.p);
+    int bad = 0;
+    SS_CUDA(cudaMemcpyAsync(&bad, sc.bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaStreamSynchronize(st));
+    SS_CUDA(cudaGetLastError());
+    SS_REQUIRE(!bad, SS_ERR_INVALID, "ss_graph_load_csr_rows: row_ptr not monotone or child id out of range");
+    return SS_OK;
+  };
+  struct Slice {
+    uint64_t lo, hi, edges;
+    int64_t status;
+  } mine{row_lo, row_hi, E_slice, 0}, all[64];
+  mine.status = local_phase();
+  SS_TRY(comm_allgather_host_bytes(e, &mine, sizeof(mine), all));
+  uint64_t covered = 0, E = 0;
+  for (int r = 0; r < world; ++r) {
+    if (all[r].status < 0) {
+      if (mine.status >= 0) ss::set_error("ss_graph_load_csr_rows: rank %d failed its local phase (%lld)", r,
+                                          (long long)all[r].status);
+      return mine.status < 0 ? (int)mine.status : SS_ERR_STATE;
+    }
+    covered += all[r].hi - all[r].lo;
+    E += all[r].edges;
   }
+  SS_REQUIRE(covered == N, SS_ERR_INVALID, "ss_graph_load_csr_rows: the ranks' slices cover %llu of %llu rows",
+             (unsigned long long)covered, (unsigned long long)N);
+  s->E = E;
+
+  // out-degree of every node (each rank contributes its slice); in-degrees summed over the slices
+  {
+    std::vector<size_t> off(world), cnt(world);
+    for (int r = 0; r < world; ++r) {
+      off[r] = all[r].lo * 4;
+      cnt[r] = (all[r].hi - all[r].lo) * 4;
+    }
+    SS_TRY(comm_allgatherv_bytes(e, s->outdeg.p, off.data(), cnt.data()));
+  }
+  SS_TRY(comm_allreduce_sum_u32(e, sc.cnt.p, N));
+  k_widen_counts<<<ss::div_up(N + 1, 256), 256, 0, st>>>(sc.cnt.p, N, sc.keys.p);
+  {
+    size_t scan_bytes = sc.tmp.n;
+    SS_CUDA(cub::DeviceScan::ExclusiveSum(sc.tmp.p, scan_bytes, sc.keys.p, sc.in_ptr_full.p, (int64_t)(N + 1), st));
+  }
+  k_partition<<<1, 64, 0, st>>>(sc.in_ptr_full.p, N, world, sc.bounds.p);
+  std::vector<unsigned long long> hb(world + 1);
+  SS_CUDA(cudaMemcpyAsync(hb.data(), sc.bounds.p, (world + 1) * 8, cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaStreamSynchronize(st));
-  SS_CUDA(cudaGetLastError());
-  s->stats = ss_pagerank_stats{};
-  s->stats.n_nodes = N;
-  s->stats.n_edges = E;
-  s->stats.row_lo = s->row_lo;
-  s->stats.local_rows = s->rows_loc;
-  s->stats.local_edges = s->E_loc;
-  s->stats.load_ms =
-      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
-  s->loaded = true;
-  return SS_OK;
+  for (int r = 0; r <= world; ++r) s->bounds[r] = hb[r];
+  s->row_lo = s->bounds[rank];
+  s->rows_loc = (uint32_t)(s->bounds[rank + 1] - s->bounds[rank]);
+
+  // all-to-all of the edges: rank q owns children [bounds[q], bounds[q+1]) = a contiguous piece of every
+  // slice's child-sorted list
+  std::vector<unsigned long long> cut(world + 1);
+  for (int r = 0; r <= world; ++r)
+    SS_CUDA(cudaMemcpyAsync(&cut[r], sc.slice_ptr.p + s->bounds[r], 8, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaStreamSynchronize(st));
+  std::vector<uint64_t> send_cnt64(world), matrix((size_t)world * world);
+  for (int r = 0; r < world; ++r) send_cnt64[r] = cut[r + 1] - cut[r];
+  SS_TRY(comm_allgather_host_bytes(e, send_cnt64.data(), world * 8, matrix.data()));
+  std::vector<size_t> send_off(world), send_cnt(world), recv_off(world), recv_cnt(world);
+  uint64_t E_loc = 0;
+  for (int r = 0; r < world; ++r) {
+    send_off[r] = cut[r];
+    send_cnt[r] = send_cnt64[r];
+    recv_off[r] = E_loc;
+    recv_cnt[r] = matrix[(size_t)r * world + rank];
+    E_loc += recv_cnt[r];
+  }
+  // second allocation round, status agreed on again
+  auto alloc2 = [&]() -> int {
+    SS_REQUIRE(E_loc < 0xFFFFFFFFull, SS_ERR_INVALID, "ss_graph_load_csr_rows: %llu local edges; use more ranks",
+               (unsigned long long)E_loc);
+    SS_TRY(sc.recv_col.reserve(E_loc));
+    SS_TRY(sc.recv_src.reserve(E_loc));
+    SS_TRY(sc.col.reserve(E_loc));
+    SS_TRY(s->in_src.reserve(E_loc));
+    SS_TRY(s->in_ptr.reserve((size_t)s->rows_loc + 1));
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, sc.recv_col.p, sc.col.p, sc.recv_src.p, s->in_src.p,
+                                    (int64_t)std::max<uint64_t>(E_loc, 1), 0, end_bit, st);
+    SS_TRY(sc.tmp.reserve(tmp_bytes));
+    return SS_OK;
+  };
+  int64_t st2 = alloc2(), all2[64];
+  SS_TRY(comm_allgather_host_bytes(e, &st2, sizeof(st2), all2));
+  for (int r = 0; r < world; ++r)
+    if (all2[r] < 0) {
+      if (st2 >= 0) ss::set_error("ss_graph_load_csr_rows: rank %d could not allocate its partition", r);
+      return st2 < 0 ? (int)st2 : SS_ERR_STATE;
+    }
+  {
+    const uint32_t* send[2] = {sc.col_sorted.p, sc.src_sorted.p};
+    uint32_t* recv[2] = {sc.recv_col.p, sc.recv_src.p};
+    SS_TRY(comm_alltoallv_u32(e, 2, send, send_off.data(), send_cnt.data(), recv, recv_off.data(), recv_cnt.data()));
+  }
+  // pieces arrive in rank order, each sorted by (child, parent): a stable sort by child leaves the parents of a
+  // row ascending when the slices ascend with the rank
+  if (E_loc) {
+    size_t tmp_bytes = sc.tmp.n;
+    SS_CUDA(cub::DeviceRadixSort::SortPairs(sc.tmp.p, tmp_bytes, sc.recv_col.p, sc.col.p, sc.recv_src.p, s->in_src.p,
+                                            (int64_t)E_loc, 0, end_bit, st));
+  }
+  s->E_loc = E_loc;
+  k_in_ptr_local<<<ss::div_up((uint64_t)s->rows_loc + 1, 256), 256, 0, st>>>(sc.col.p, E_loc, s->row_lo, s->rows_loc,
+                                                                            s->in_ptr.p);
+  return finish_load(e, s, t_begin);
 }
 
 SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topics, const int64_t* num_pages,
@@ -1343,6 +1674,7 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
   s->stats.sweeps = 0;
   s->stats.launches = 0;
   s->stats.sweep_ms_total = s->stats.gather_ms_total = s->stats.exchange_ms_total = s->stats.short_ms_total = 0;
+  s->stats.exchange_busy_ms_total = 0;
   if (n_topics == 0) {  // empty forw[5]: every node gets {} (pagerank.go:53-63)
     s->T = 0;
     s->have_result = true;
@@ -1405,11 +1737,35 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
     SS_TRY(s->warp_rows.reserve((size_t)n_warps + 1));
     k_short_partition<<<ss::div_up((uint64_t)n_warps + 1, 256), 256, 0, st>>>(s->sptr.p, R, n_warps, s->warp_rows.p);
   }
-  const uint32_t grid_long = std::max(
-      1u, std::min<uint32_t>(ss::div_up(s->n_tasks, kThreads / 32), (uint32_t)(e->sm_count * std::max(1, occ_long))));
-  const uint32_t grid_fix = std::max(1u, std::min<uint32_t>(s->n_fix, (uint32_t)e->sm_count * 8));
+  // Per-chunk launch shapes (one chunk unless the exchange is overlapped, see PagerankState::n_chunks).
+  // Chunking needs the lean short-row kernel (the others walk the whole row range).
+  const bool chunked = s->n_chunks > 1 && lean && !use_async && world > 1;
+  const int C = chunked ? s->n_chunks : 1;
+  struct ChunkShape {
+    uint32_t row_begin, row_end, n_row_blocks, grid_short, task_begin, n_tasks, grid_long, fix_begin, n_fix, grid_fix;
+    uint32_t slot0;  // first reduction slot of the chunk's three launches
+  };
+  std::vector<ChunkShape> chunks(C);
+  uint32_t sweep_slots = 0;
+  for (int c = 0; c < C; ++c) {
+    ChunkShape& k = chunks[c];
+    k.row_begin = chunked ? s->chunk_rows[c] : 0u;
+    k.row_end = chunked ? s->chunk_rows[c + 1] : R;
+    k.n_row_blocks = ss::div_up(k.row_end - k.row_begin, GPC);
+    k.grid_short = chunked ? std::max(1u, std::min<uint32_t>(k.n_row_blocks, (uint32_t)(e->sm_count * std::max(1, occ_short))))
+                           : grid_short;
+    k.task_begin = chunked ? s->chunk_task[c] : 0u;
+    k.n_tasks = chunked ? s->chunk_task[c + 1] - s->chunk_task[c] : s->n_tasks;
+    k.grid_long = std::max(1u, std::min<uint32_t>(ss::div_up(k.n_tasks, kThreads / 32),
+                                                  (uint32_t)(e->sm_count * std::max(1, occ_long))));
+    k.fix_begin = chunked ? s->chunk_fix[c] : 0u;
+    k.n_fix = chunked ? s->chunk_fix[c + 1] - s->chunk_fix[c] : s->n_fix;
+    k.grid_fix = std::max(1u, std::min<uint32_t>(k.n_fix, (uint32_t)e->sm_count * 8));
+    k.slot0 = sweep_slots;
+    sweep_slots += k.grid_short + k.grid_long + k.grid_fix;
+  }
   const uint32_t grid_init = (uint32_t)e->sm_count * 8;
-  const uint32_t red_slots = std::max(grid_short + grid_long + grid_fix, grid_init);
+  const uint32_t red_slots = std::max(sweep_slots, grid_init);
   const int W = 3 * TP;
 
   if (world > 1) {  // fixed-size state so that the peer mappings survive topic-count changes
@@ -1430,16 +1786,33 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
   SS_TRY(s->tot.reserve(TP));
   SS_TRY(s->init.reserve(TP));
 
+  const bool biased = s->tele_T != 0;
+  if (biased) {
+    SS_REQUIRE(s->tele_T == n_topics, SS_ERR_INVALID, "ss_pagerank: teleport weights were set for %u topics, run has %u",
+               s->tele_T, n_topics);
+    SS_TRY(s->tele_w.reserve((size_t)R * TP));
+    if (R) k_pad_rows<<<ss::div_up((uint64_t)R * TP, 256), 256, 0, st>>>(s->tele_raw.p, R, T, TP, s->tele_w.p);
+  }
   double h_init[16];
   for (int t = 0; t < TP; ++t) h_init[t] = t < T ? 1.0 / (double)num_pages[t] : 0.0;  // pagerank.go:104
   SS_CUDA(cudaMemcpyAsync(s->init.p, h_init, TP * 8, cudaMemcpyHostToDevice, st));
 
   const double tele = 1.0 - damping;  // pagerank.go:90
-  std::vector<size_t> byte_off(world), byte_cnt(world);
-  for (int r = 0; r < world; ++r) {
-    byte_off[r] = (size_t)s->bounds[r] * TP * 8;
-    byte_cnt[r] = (size_t)(s->bounds[r + 1] - s->bounds[r]) * TP * 8;
+  // exchange layout: every rank's row block, cut into the same number of chunks on every rank
+  std::vector<uint64_t> all_rows((size_t)world * (C + 1));
+  if (world > 1) {
+    std::vector<uint64_t> mine(C + 1);
+    for (int c = 0; c <= C; ++c) mine[c] = s->row_lo + (chunked ? s->chunk_rows[c] : (c == C ? R : 0u));
+    SS_TRY(comm_allgather_host_bytes(e, mine.data(), (C + 1) * 8, all_rows.data()));
   }
+  std::vector<size_t> byte_off(world), byte_cnt(world);
+  auto chunk_bytes = [&](int c) {
+    for (int r = 0; r < world; ++r) {
+      const uint64_t lo = all_rows[(size_t)r * (C + 1) + c], hi = all_rows[(size_t)r * (C + 1) + c + 1];
+      byte_off[r] = (size_t)lo * TP * 8;
+      byte_cnt[r] = (size_t)(hi - lo) * TP * 8;
+    }
+  };
 
   // y0, mul, S_0
   int rc = dispatch_shape(shape, [&](auto lpr, auto vec) {
@@ -1475,7 +1848,9 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
     p.warp_rows = s->warp_rows.p;
     p.inv_tot = s->tot.p;
     p.init = s->init.p;
+    p.tele_w = biased ? s->tele_w.p : nullptr;
     p.row_lo = s->row_lo;
+    p.row_begin = 0;
     p.rows_loc = R;
     p.active_mask = active;
     p.tele = tele;
@@ -1483,54 +1858,76 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
     p.n_peers = s->fused ? s->n_peers : 0;
     for (int q = 0; q < kMaxPeers; ++q) p.peer_next[q] = s->fused ? s->peer_y[s->cur ^ 1][q] : nullptr;
     if (timing) SS_CUDA(cudaEventRecord(s->ev[0], st));
-    rc = dispatch_shape(shape, [&](auto lpr, auto vec) {
-      constexpr int L = decltype(lpr)::value, V = decltype(vec)::value;
-      SweepParams q = p;
-      q.red = s->red.p;
-      const bool all = active == all_topics && T == TP;  // padded columns stay frozen through the mask
-      if (use_async) {
-        if (p.first) {
-          if (all) k_sweep_short_async<L, true, true><<<grid_short, kAsyncThreads, async_smem, st>>>(q);
-          else k_sweep_short_async<L, true, false><<<grid_short, kAsyncThreads, async_smem, st>>>(q);
+    const bool overlap = world > 1 && !s->fused;  // NCCL exchange on its own stream, chunk by chunk
+    for (int c = 0; c < C; ++c) {
+      const ChunkShape& k = chunks[c];
+      rc = dispatch_shape(shape, [&](auto lpr, auto vec) {
+        constexpr int L = decltype(lpr)::value, V = decltype(vec)::value;
+        SweepParams q = p;
+        q.row_begin = k.row_begin;
+        q.rows_loc = k.row_end;
+        q.red = s->red.p + (size_t)k.slot0 * W;
+        const bool all = active == all_topics && T == TP;  // padded columns stay frozen through the mask
+        if (use_async) {
+          if (p.first) {
+            if (all) k_sweep_short_async<L, true, true><<<k.grid_short, kAsyncThreads, async_smem, st>>>(q);
+            else k_sweep_short_async<L, true, false><<<k.grid_short, kAsyncThreads, async_smem, st>>>(q);
+          } else {
+            if (all) k_sweep_short_async<L, false, true><<<k.grid_short, kAsyncThreads, async_smem, st>>>(q);
+            else k_sweep_short_async<L, false, false><<<k.grid_short, kAsyncThreads, async_smem, st>>>(q);
+          }
+        } else if (lean) {
+          if (p.first) {
+            if (all) k_sweep_short32<L, V, true, true><<<k.grid_short, kThreads, 0, st>>>(q, k.n_row_blocks);
+            else k_sweep_short32<L, V, true, false><<<k.grid_short, kThreads, 0, st>>>(q, k.n_row_blocks);
+          } else {
+            if (all) k_sweep_short32<L, V, false, true><<<k.grid_short, kThreads, 0, st>>>(q, k.n_row_blocks);
+            else k_sweep_short32<L, V, false, false><<<k.grid_short, kThreads, 0, st>>>(q, k.n_row_blocks);
+          }
         } else {
-          if (all) k_sweep_short_async<L, false, true><<<grid_short, kAsyncThreads, async_smem, st>>>(q);
-          else k_sweep_short_async<L, false, false><<<grid_short, kAsyncThreads, async_smem, st>>>(q);
+          k_sweep_short<L, V><<<k.grid_short, kThreads, 0, st>>>(q, k.n_row_blocks);
         }
-      } else if (lean) {
-        if (p.first) {
-          if (all) k_sweep_short32<L, V, true, true><<<grid_short, kThreads, 0, st>>>(q, n_row_blocks);
-          else k_sweep_short32<L, V, true, false><<<grid_short, kThreads, 0, st>>>(q, n_row_blocks);
-        } else {
-          if (all) k_sweep_short32<L, V, false, true><<<grid_short, kThreads, 0, st>>>(q, n_row_blocks);
-          else k_sweep_short32<L, V, false, false><<<grid_short, kThreads, 0, st>>>(q, n_row_blocks);
-        }
-      } else {
-        k_sweep_short<L, V><<<grid_short, kThreads, 0, st>>>(q, n_row_blocks);
+        if (timing && c == C - 1) cudaEventRecord(s->ev[4], st);
+        q.rows_loc = R;
+        q.red = s->red.p + (size_t)(k.slot0 + k.grid_short) * W;
+        k_sweep_long<L, V><<<k.grid_long, kThreads, 0, st>>>(q, s->tasks.p + k.task_begin, k.n_tasks, s->partials.p);
+        if (timing && c == C - 1) cudaEventRecord(s->ev[1], st);
+        q.red = s->red.p + (size_t)(k.slot0 + k.grid_short + k.grid_long) * W;
+        k_sweep_fix<L, V><<<k.grid_fix, kThreads, 0, st>>>(q, s->fix.p + k.fix_begin, k.n_fix, s->partials.p);
+        return SS_OK;
+      });
+      SS_TRY(rc);
+      s->stats.launches += 3;
+      if (overlap) {
+        // chunk c of every rank is final: ship it while the next chunk computes
+        SS_CUDA(cudaEventRecord(s->chunk_ev[c], st));
+        SS_CUDA(cudaStreamWaitEvent(s->xstream, s->chunk_ev[c], 0));
+        if (timing && c == 0) SS_CUDA(cudaEventRecord(s->x_t0, s->xstream));
+        chunk_bytes(c);
+        SS_TRY(comm_allgatherv_bytes_on(e, s->xstream, p.y_next, byte_off.data(), byte_cnt.data()));
       }
-      if (timing) cudaEventRecord(s->ev[4], st);
-      q.red = s->red.p + (size_t)grid_short * W;
-      k_sweep_long<L, V><<<grid_long, kThreads, 0, st>>>(q, s->tasks.p, s->n_tasks, s->partials.p);
-      if (timing) cudaEventRecord(s->ev[1], st);
-      q.red = s->red.p + (size_t)(grid_short + grid_long) * W;
-      k_sweep_fix<L, V><<<grid_fix, kThreads, 0, st>>>(q, s->fix.p, s->n_fix, s->partials.p);
-      return SS_OK;
-    });
-    SS_TRY(rc);
-    k_reduce_partials<<<kReduceCtas, kThreads, 0, st>>>(s->red.p, grid_short + grid_long + grid_fix, W, s->stage.p);
+    }
+    k_reduce_partials<<<kReduceCtas, kThreads, 0, st>>>(s->red.p, sweep_slots, W, s->stage.p);
     k_fold_stage<<<1, 64, 0, st>>>(s->stage.p, kReduceCtas, W, s->sums.p);
     if (timing) SS_CUDA(cudaEventRecord(s->ev[2], st));
     if (world > 1) {
-      // fused: rows were pushed by the epilogue; the all-reduce below doubles as the barrier that
-      // orders every rank's pushes before anybody's next sweep
-      if (!s->fused) SS_TRY(comm_allgatherv_bytes(e, p.y_next, byte_off.data(), byte_cnt.data()));
-      SS_TRY(comm_allreduce_sum_f64(e, s->sums.p, W));
+      // every NCCL call of the loop goes to the exchange stream, in the same order on every rank; the
+      // all-reduce of the 3*TP sums closes the sweep (fused exchange: it is also the barrier that orders
+      // every rank's pushed rows before anybody's next sweep)
+      SS_CUDA(cudaEventRecord(s->red_done, st));
+      SS_CUDA(cudaStreamWaitEvent(s->xstream, s->red_done, 0));
+      if (timing && !overlap) SS_CUDA(cudaEventRecord(s->x_t0, s->xstream));
+      SS_TRY(comm_allreduce_sum_f64_on(e, s->xstream, s->sums.p, W));
+      if (timing) SS_CUDA(cudaEventRecord(s->x_t1, s->xstream));
+      SS_CUDA(cudaEventRecord(s->x_done, s->xstream));
+      SS_CUDA(cudaStreamWaitEvent(st, s->x_done, 0));
     }
     k_finish_tot<<<1, 32, 0, st>>>(s->sums.p, TP, tele, (double)N, s->tot.p);
     if (timing) SS_CUDA(cudaEventRecord(s->ev[3], st));
     SS_CUDA(cudaMemcpyAsync(h_sums.data(), s->sums.p, W * 8, cudaMemcpyDeviceToHost, st));
     SS_CUDA(cudaStreamSynchronize(st));
     SS_CUDA(cudaGetLastError());
-    s->stats.launches += 6;
+    s->stats.launches += 3;
     s->stats.sweeps = sweep;
     if (timing) {
       float ms = 0;
@@ -1541,7 +1938,11 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
       cudaEventElapsedTime(&ms, s->ev[0], s->ev[4]);
       s->stats.short_ms_total += ms;
       cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]);
-      s->stats.exchange_ms_total += ms;
+      s->stats.exchange_ms_total += ms;  // what the sweep loop waits for after its own kernels (exposed)
+      if (world > 1) {
+        cudaEventElapsedTime(&ms, s->x_t0, s->x_t1);
+        s->stats.exchange_busy_ms_total += ms;  // first chunk broadcast .. end of the all-reduce
+      }
     }
     s->cur ^= 1;
     for (int t = 0; t < T; ++t) {
@@ -1561,21 +1962,34 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
   s->have_result = true;
   if (out_iters) memcpy(out_iters, iters.data(), T * sizeof(uint32_t));
   if (out_rank && N) {
-    // the state is replicated on every rank after the exchange: unscale all rows
-    // in bounded chunks and copy them out
-    const uint64_t chunk_rows = std::max<uint64_t>(1, (64ull << 20) / ((uint64_t)T * 8));
-    ss::DevBuf<double>& stage = s->out_stage[0];
-    SS_TRY(stage.reserve(std::min<uint64_t>(chunk_rows, N) * T));
-    for (uint64_t lo = 0; lo < N; lo += chunk_rows) {
-      const uint64_t hi = std::min<uint64_t>(lo + chunk_rows, N);
-      const uint64_t total = (hi - lo) * T;
-      k_unscale<<<ss::div_up(total, 256), 256, 0, st>>>(s->y[s->cur].p, s->outdeg.p, damping, TP, T, lo, hi, stage.p);
-      SS_CUDA(cudaMemcpyAsync(out_rank + lo * T, stage.p, total * 8, cudaMemcpyDeviceToHost, st));
-      SS_CUDA(cudaStreamSynchronize(st));
-      s->stats.launches += 1;
-    }
+    // the state is replicated on every rank after the exchange: unscale every row into the idle state
+    // buffer (same or smaller footprint: [N][T] vs [N][TP]) and copy it out in one piece -- no staging
+    // chunks, no host round trip per chunk
+    SS_TRY(unscale_and_copy(e, s, 0, N, out_rank));
   }
   return hit_max ? SS_NOT_CONVERGED : SS_OK;
+}
+
+SS_API int ss_pagerank_set_teleport(ss_engine* e, uint64_t n_nodes, uint32_t n_topics, const double* weight) {
+  SS_REQUIRE(e, SS_ERR_INVALID, "ss_pagerank_set_teleport: engine is NULL");
+  std::lock_guard<std::mutex> lock(e->mu);
+  DeviceGuard guard(e->device);
+  PagerankState* s = e->pr;
+  SS_REQUIRE(s && s->loaded, SS_ERR_STATE, "ss_pagerank_set_teleport: load the graph first");
+  if (!weight || n_topics == 0) {
+    s->tele_T = 0;
+    return SS_OK;
+  }
+  SS_REQUIRE(n_nodes == s->N, SS_ERR_INVALID, "ss_pagerank_set_teleport: %llu rows, graph has %llu",
+             (unsigned long long)n_nodes, (unsigned long long)s->N);
+  SS_REQUIRE(n_topics <= 16, SS_ERR_INVALID, "ss_pagerank_set_teleport: at most 16 topics per run");
+  const size_t n = (size_t)s->rows_loc * n_topics;
+  SS_TRY(s->tele_raw.reserve(n));
+  if (n)  // this rank's rows are one contiguous piece of the caller's [N][T] array
+    SS_CUDA(cudaMemcpyAsync(s->tele_raw.p, weight + s->row_lo * n_topics, n * 8, cudaMemcpyHostToDevice, e->stream));
+  SS_CUDA(cudaStreamSynchronize(e->stream));
+  s->tele_T = n_topics;
+  return SS_OK;
 }
 
 SS_API int ss_pagerank_fetch(ss_engine* e, uint64_t row_lo, uint64_t row_hi, double* out_rank) {
@@ -1586,19 +2000,7 @@ SS_API int ss_pagerank_fetch(ss_engine* e, uint64_t row_lo, uint64_t row_hi, dou
   SS_REQUIRE(s && s->have_result, SS_ERR_STATE, "ss_pagerank_fetch: no result");
   SS_REQUIRE(row_lo <= row_hi && row_hi <= s->N, SS_ERR_INVALID, "ss_pagerank_fetch: bad row range");
   if (s->T == 0 || row_lo == row_hi) return SS_OK;
-  cudaStream_t st = e->stream;
-  const int T = s->T;
-  const uint64_t chunk_rows = std::max<uint64_t>(1, (64ull << 20) / ((uint64_t)T * 8));
-  ss::DevBuf<double>& stage = s->out_stage[0];
-  SS_TRY(stage.reserve(std::min<uint64_t>(chunk_rows, row_hi - row_lo) * T));
-  for (uint64_t lo = row_lo; lo < row_hi; lo += chunk_rows) {
-    const uint64_t hi = std::min<uint64_t>(lo + chunk_rows, row_hi);
-    const uint64_t total = (hi - lo) * T;
-    k_unscale<<<ss::div_up(total, 256), 256, 0, st>>>(s->y[s->cur].p, s->outdeg.p, s->damping, s->TP, T, lo, hi,
-                                                      stage.p);
-    SS_CUDA(cudaMemcpyAsync(out_rank + (lo - row_lo) * T, stage.p, total * 8, cudaMemcpyDeviceToHost, st));
-    SS_CUDA(cudaStreamSynchronize(st));
-  }
+  SS_TRY(unscale_and_copy(e, s, row_lo, row_hi, out_rank));
   return SS_OK;
 }
 

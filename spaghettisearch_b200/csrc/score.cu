@@ -453,6 +453,7 @@ static int build_dense_vectors(ss_engine* e, IndexState* ix, cudaStream_t st, ui
   const uint64_t d_pad = (D + kDenseRange - 1) / kDenseRange * kDenseRange + kDensePadDocs;
   if (!ix->dense_valid) {
     ix->n_dense = 0;
+    ix->dense_host.clear();
     const uint64_t V = std::max(ix->tab[0].loaded ? ix->tab[0].V : 0, ix->tab[1].loaded ? ix->tab[1].V : 0);
     if (V && max_dense) {
       constexpr uint32_t cap = 4096;
@@ -504,6 +505,8 @@ static int build_dense_vectors(ss_engine* e, IndexState* ix, cudaStream_t st, ui
       }
       ix->n_dense = nd;
       ix->dense_map_V = V;
+      ix->dense_host.assign(V, 0);
+      for (uint32_t i = 0; i < nd; ++i) ix->dense_host[chosen[i]] = 1;
     }
     ix->d_pad = d_pad;
     ix->dense_valid = true;
@@ -778,6 +781,38 @@ static int score_batch_core(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, 
   unsigned long long h_stats[2] = {0, 0};
   SS_CUDA(cudaMemcpyAsync(h_stats, ws.stats.p, 16, cudaMemcpyDeviceToHost, st));
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[3], st));
+  // Byte model of what this batch has to move on the path it takes (host arithmetic while the kernels run):
+  // a query with a dense keyword streams 2 B per doc for each dense token and for the blend bound and reads
+  // 8 B per posting of its other tokens; any other query reads 8 B per posting of all its lists.
+  uint64_t model_bytes = 12ull * k * n_q;
+  {
+    const bool dense_on = use_dense && ix->dense_valid && ix->n_dense && !ix->dense_host.empty();
+    auto df_of = [&](uint32_t term) -> uint64_t {
+      uint64_t d = 0;
+      for (int tb = 0; tb < 2; ++tb)
+        if (ix->tab[tb].loaded && term < ix->tab[tb].df_host.size()) d += ix->tab[tb].df_host[term];
+      return d;
+    };
+    for (uint64_t q = 0; q < n_q; ++q) {
+      uint64_t n_dense_tok = 0, sparse_postings = 0, all_postings = 0;
+      bool dense_kw = false;
+      auto visit = [&](uint32_t term, bool is_kw) {
+        const uint64_t df = df_of(term);
+        all_postings += df;
+        if (dense_on && term < ix->dense_host.size() && ix->dense_host[term]) {
+          ++n_dense_tok;
+          dense_kw = dense_kw || is_kw;
+        } else {
+          sparse_postings += df;
+        }
+      };
+      for (uint64_t i = kw_ptr[q]; i < kw_ptr[q + 1]; ++i) visit(kw_terms[i], true);
+      if (ph_ptr)
+        for (uint64_t i = ph_ptr[q]; i < ph_ptr[q + 1]; ++i) visit(ph_terms[i], false);
+      model_bytes += dense_kw ? 2ull * D * (n_dense_tok + 1) + 8ull * sparse_postings : 8ull * all_postings;
+    }
+  }
+  ix->stats.model_bytes = model_bytes;
   SS_CUDA(cudaStreamSynchronize(st));
   SS_CUDA(cudaGetLastError());
   ix->stats.postings_scanned = h_stats[0];
@@ -883,6 +918,7 @@ static int score_batch_entry(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr,
     total.kernel_ms += st.kernel_ms;
     total.score_kernel_ms += st.score_kernel_ms;
     total.shard_merge_ms += st.shard_merge_ms;
+    total.model_bytes += st.model_bytes;
   }
   e->idx->stats = total;
   return SS_OK;

@@ -160,3 +160,32 @@ def test_million_node_graph_against_fair_oracle(engine):
     _check(engine, g.row_ptr, g.col_idx, 0.75, 1e-9, synth.topics(16), fair_threads=8)
     st = engine.pagerank_stats()
     assert st.sweeps >= 3 and st.launches > 0 and st.sweep_ms_total > 0
+
+
+def test_topic_biased_teleport_extension(engine):
+    """SURVEY.md 8(f)-4 (opt-in, beyond the shipped reference): per-topic teleport vectors.  All-ones weights are
+    the reference's uniform teleport bit for bit; a genuinely biased vector matches the oracle's extension."""
+    n = 30000
+    g = synth.graph(n, 400000, seed=5)
+    npg = synth.topics(6)
+    engine.graph_load_csr(g.row_ptr, g.col_idx)
+    base, it0, _ = engine.pagerank(0.75, 1e-9, npg)
+    engine.pagerank_set_teleport(np.ones((n, 6)))
+    same, it1, _ = engine.pagerank(0.75, 1e-9, npg)
+    assert np.array_equal(base, same) and it0.tolist() == it1.tolist()
+    rng = np.random.default_rng(2)
+    w = np.zeros((n, 6))
+    for t in range(6):  # topic t teleports only to its own page set (Haveliwala), weights sum to n per topic
+        pages = rng.choice(n, size=500 + 100 * t, replace=False)
+        w[pages, t] = n / len(pages)
+    engine.pagerank_set_teleport(w)
+    got, iters, status = engine.pagerank(0.75, 1e-9, npg)
+    ref, it_ref = O.pagerank_biased(g.row_ptr, g.col_idx, 0.75, 1e-9, npg, w)
+    assert status == 0 and iters.tolist() == it_ref.tolist()
+    assert np.abs(got - ref).sum(axis=0).max() <= 1e-9
+    assert np.abs(got - base).sum() > 1e-3  # it really is a different ranking
+    with pytest.raises(capi.SSError):
+        engine.pagerank(0.75, 1e-9, npg[:4])  # weights were set for 6 topics
+    engine.pagerank_set_teleport(None)
+    again, _, _ = engine.pagerank(0.75, 1e-9, npg)
+    assert np.array_equal(base, again)
