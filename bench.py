@@ -144,7 +144,43 @@ def pr_grid(world, spec):
     return {1: (1, 1), 2: (2, 1), 4: (4, 1), 8: (4, 2)}.get(world, (world, 1))
 
 
+def run_c1(args):
+    """BASELINE.json configs[0]: 10k pages / 50k terms / 100 queries written in the reference's JSON table
+    encodings and run through the C++ host mirror of the three Go-API calls (csrc/host/), checked against
+    the oracle.  Reports the wall-clock seconds per call (JSON decode/encode included) next to the oracle's."""
+    import tempfile
+    from tests import c1_workload as c1
+    from spaghettisearch_b200 import capi
+    eng = capi.Engine(device=0, timing=True)
+    with tempfile.TemporaryDirectory() as d:
+        tmp = Path(d)
+        w = c1.make_tables(tmp)
+        c1.run(eng, tmp, w)  # warm-up: allocations, the impact vectors of the first batch
+        results, times = c1.run(eng, tmp, w)
+        info = c1.check(tmp, w, results)
+    eng.close()
+    total = sum(v for k, v in times.items() if k != "load_snapshots")
+    cpu_total = sum(info["cpu_seconds"].values())
+    print(json.dumps({
+        "metric": "c1_go_api_seconds", "value": total, "unit": "s", "n_gpus": 1, "steps": 1, "warmup": 1,
+        "ms_per_step": total * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 / f32 as the reference", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[0]: 10k-page link graph + 50k-term index in the reference's "
+                               "JSON table encodings, UpdateTopicSensitivePagerank + UpdateTermWeights x2 + "
+                               "Retrieve x100 through the host mirror of the Go API"},
+        "seconds_per_call": times,
+        "parity": dict(info, ok=True, against="oracle on the equivalent dense arrays: forw[3] within 1e-9 L1, "
+                       "forw[4] bit-exact, result lists identical up to ties, scores within 1e-6"),
+        "cpu_baseline": {"value": cpu_total, "unit": "s", "cores": 1, "kind": "port",
+                         "sample": "the oracle on the dense arrays (no JSON): " + json.dumps(info["cpu_seconds"])},
+        "e2e": {"value": total, "unit": "s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                "what": "table snapshots in host memory -> JSON decode -> C ABI -> JSON encode"},
+        "gpu_launches": None}), flush=True)
+
+
 def run_ours(args):
+    if args.workload == "c1":
+        return run_c1(args)
     import torch
     import torch.distributed as dist
     from spaghettisearch_b200 import capi, sharding, synth
@@ -337,15 +373,16 @@ def run_pagerank(args, ctx):
                    "partition": (f"{rg} row groups x {tg} topic groups; rows edge-balanced; sharded export "
                                  "(ss_graph_load_csr_rows: one all-to-all of the edges at load)") if world > 1
                                 else "single GPU",
-                   "collective": ("per sweep inside a row group: grouped ncclBroadcast (all-gather-v) of the row "
-                                  "blocks, chunked and overlapped with the sweep on an exchange stream, + "
-                                  "ncclAllReduce of 3*T sums" if rg > 2 else
+                   "collective": ("per sweep inside a row group: every rank pushes its finished row chunks into the "
+                                  "peers' state with copy-engine peer copies over NVLink (CUDA IPC), overlapped with "
+                                  "the sweep of the next chunk on an exchange stream (SS_PR_EXCHANGE=nccl: grouped "
+                                  "ncclBroadcast instead), + ncclAllReduce of 3*T sums as the barrier" if rg > 2 else
                                   "2-rank row group: sweep epilogue pushes rows into the peer's state over NVLink "
                                   "(CUDA IPC peer memory), ncclAllReduce of 3*T sums as the barrier" if rg == 2 else
                                   "none (topics are independent)")},
         "clocks": clocks,
         "e2e": {"value": e2e_gteps, "unit": "GTEPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s * 1e3 / e2e_steps,
+                "ms_per_step": e2e_s * 1e3 / e2e_steps, "load_ms": eng.pagerank_stats().load_ms,
                 "what": "ss_graph_load_csr_rows (pinned host CSR slice, device transpose, edge exchange) + "
                         "ss_pagerank + this rank's rows to pinned host memory; bytes are per rank"},
         "gpu_launches": launches,
@@ -702,7 +739,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["both", "pagerank", "scoring"], default="both")
+    ap.add_argument("--workload", choices=["both", "pagerank", "scoring", "c1"], default="both")
     ap.add_argument("--nodes", type=int, default=10_000_000, help="graph nodes per GPU")
     ap.add_argument("--edges", type=int, default=150_000_000, help="graph edges per GPU")
     ap.add_argument("--docs", type=int, default=10_000_000, help="index docs per GPU")

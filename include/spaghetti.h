@@ -169,6 +169,18 @@ SS_API int ss_set_pagerank(ss_engine* e, uint64_t n_docs, uint32_t n_topics, con
 /* Use the device-resident result of the last ss_pagerank (node id == doc id). */
 SS_API int ss_use_pagerank(ss_engine* e);
 
+/* Extension beyond the reference as shipped: live topic probabilities, i.e. the dead
+ * computeTopicProbs (retrieval/main_retrieve.go:106-159) with its defects repaired (see csrc/topics.cu).
+ * ss_topics_load: inv[2] as CSR over its own dense term ids -- row of term w = (topic id, frequency) pairs --
+ * and forw[5]'s wordCount per topic.  ss_topic_probs: for each query's keyword tokens (ids in inv[2]'s term
+ * space, unknown word = id >= n_terms) the naive-Bayes value prod_i(freq_i[t] / wordCount[t]) / n_topics over
+ * the tokens that list topic t, 0 if none does; out_probs [n_q][n_topics] is what ss_score_batch takes as
+ * topic_probs with probs_per_query = 1. */
+SS_API int ss_topics_load(ss_engine* e, uint64_t n_terms, uint32_t n_topics, const uint64_t* term_ptr,
+                          const uint32_t* topic_ids, const double* freq, const double* word_count);
+SS_API int ss_topic_probs(ss_engine* e, uint64_t n_q, const uint64_t* tok_ptr, const uint32_t* tok_terms,
+                          double* out_probs);
+
 /* Query q: keyword tokens kw_terms[kw_ptr[q] .. kw_ptr[q+1]) (duplicates kept,
  * main_retrieve.go:61-69) and one concatenated phrase ph_terms[ph_ptr[q] ..)
  * (main_retrieve.go:26; ph_ptr NULL => no phrases).  A term id >= n_terms is

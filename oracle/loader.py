@@ -159,6 +159,24 @@ def pagerank_biased(row_ptr, col_idx, damping, eps, num_pages, tele_w, max_iters
     return rank, iters
 
 
+def topic_probs(term_ptr, topic_ids, freq, word_count, tok_ptr, tok_terms):
+    """Extension: the repaired computeTopicProbs -> [Q][T]."""
+    term_ptr = np.ascontiguousarray(term_ptr, dtype=np.uint64)
+    topic_ids = np.ascontiguousarray(topic_ids, dtype=np.uint32)
+    freq = np.ascontiguousarray(freq, dtype=np.float64)
+    word_count = np.ascontiguousarray(word_count, dtype=np.float64)
+    tok_ptr = np.ascontiguousarray(tok_ptr, dtype=np.uint64)
+    tok_terms = np.ascontiguousarray(tok_terms, dtype=np.uint32)
+    nq, t = len(tok_ptr) - 1, len(word_count)
+    out = np.zeros((nq, t), dtype=np.float64)
+    L = lib()
+    L.oracle_topic_probs.argtypes = [C.c_uint64, C.c_uint32] + [C.c_void_p] * 4 + [C.c_uint64] + [C.c_void_p] * 3
+    L.oracle_topic_probs.restype = C.c_int
+    L.oracle_topic_probs(len(term_ptr) - 1, t, _p(term_ptr), _p(topic_ids), _p(freq), _p(word_count), nq, _p(tok_ptr),
+                         _p(tok_terms), _p(out))
+    return out
+
+
 def pagerank_fair_csc(row_ptr, in_ptr, in_src, damping, eps, num_pages, max_iters=0, fixed_iters=0,
                       n_threads=0, want_rank=True):
     """Fair CPU arm on a prebuilt in-edge CSC -> (rank or None, iters, seconds in the sweeps)."""

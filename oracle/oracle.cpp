@@ -668,3 +668,31 @@ extern "C" int oracle_score_batch_fair(const oracle_table* title, const oracle_t
   }
   return 0;
 }
+
+// ---- extension: live topic probabilities -------------------------------------------------
+// computeTopicProbs (retrieval/main_retrieve.go:106-159) restated with its defects repaired: `probs` starts at
+// 1 (as shipped it starts at 0 and stays 0, :142-145); inv[2] rows are found by the word's own id.  Everything
+// else as written: only tokens whose row lists the topic contribute a factor freq / wordCount[topic] (:116-134,
+// :144), token order, a topic nobody lists gets 0 (:149-151), uniform prior 1 / #topics applied last (:147).
+extern "C" int oracle_topic_probs(uint64_t n_terms, uint32_t n_topics, const uint64_t* term_ptr,
+                                  const uint32_t* topic_ids, const double* freq, const double* word_count,
+                                  uint64_t n_q, const uint64_t* tok_ptr, const uint32_t* tok_terms,
+                                  double* out_probs) {
+  for (uint64_t q = 0; q < n_q; ++q)
+    for (uint32_t t = 0; t < n_topics; ++t) {
+      double probs = 1.0;
+      bool any = false;
+      for (uint64_t k = tok_ptr[q]; k < tok_ptr[q + 1]; ++k) {
+        const uint32_t term = tok_terms[k];
+        if (term >= n_terms) continue;
+        for (uint64_t x = term_ptr[term]; x < term_ptr[term + 1]; ++x)
+          if (topic_ids[x] == t) {
+            probs *= (freq[x] / word_count[t]);
+            any = true;
+            break;
+          }
+      }
+      out_probs[q * n_topics + t] = any ? probs / (double)n_topics : 0.0;
+    }
+  return 0;
+}

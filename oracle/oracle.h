@@ -118,6 +118,12 @@ int oracle_score_batch_fair(const oracle_table* title, const oracle_table* body,
 /* retrieval/util.go:179-203 on its own (sorted multiset intersection). */
 uint64_t oracle_intersect(float* a, uint64_t na, float* b, uint64_t nb, float* out);
 
+/* Extension: computeTopicProbs (retrieval/main_retrieve.go:106-159) with probs starting at
+ * 1 instead of 0; inv[2] as CSR over its own term ids. */
+int oracle_topic_probs(uint64_t n_terms, uint32_t n_topics, const uint64_t* term_ptr,
+                       const uint32_t* topic_ids, const double* freq, const double* word_count,
+                       uint64_t n_q, const uint64_t* tok_ptr, const uint32_t* tok_terms, double* out_probs);
+
 #ifdef __cplusplus
 }
 #endif

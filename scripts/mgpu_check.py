@@ -23,7 +23,8 @@ npg = synth.topics(16)
 ref, it_ref, _ = O.pagerank_fair(row_ptr, col_idx, 0.75, 1e-9, npg, n_threads=4)
 ok_pr = True
 for load, env in (("full", {}), ("rows", {}), ("rows", {"SS_PR_EXCHANGE": "nccl", "SS_PR_CHUNKS": "4"}),
-                  ("full", {"SS_PR_EXCHANGE": "nccl", "SS_PR_CHUNKS": "3"}), ("rows", {"SS_PR_EXCHANGE": "nccl"})):
+                  ("full", {"SS_PR_EXCHANGE": "nccl", "SS_PR_CHUNKS": "3"}), ("rows", {"SS_PR_EXCHANGE": "nccl"}),
+                  ("rows", {"SS_PR_EXCHANGE": "copy", "SS_PR_CHUNKS": "4"}), ("full", {"SS_PR_EXCHANGE": "copy"})):
     os.environ.update(env)
     if load == "full":
         eng.graph_load_csr(row_ptr, col_idx)

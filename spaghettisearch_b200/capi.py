@@ -23,7 +23,7 @@ EXPORTS = [
     "ss_graph_load_csr", "ss_graph_load_csr_rows", "ss_pagerank", "ss_pagerank_fetch", "ss_pagerank_set_teleport", "ss_pagerank_get_stats", "ss_index_load",
     "ss_index_clear", "ss_index_set_doc_base", "ss_score_batch_sharded",
     "ss_term_weights", "ss_set_doc_norms", "ss_set_pagerank", "ss_use_pagerank", "ss_score_batch",
-    "ss_merge_topk", "ss_score_get_stats",
+    "ss_merge_topk", "ss_score_get_stats", "ss_topics_load", "ss_topic_probs",
 ]
 
 
@@ -94,6 +94,8 @@ def load():
     L.ss_score_batch.argtypes = [vp, u64, vp, vp, vp, vp, vp, i32, u32, vp, vp, vp, vp]
     L.ss_score_batch_sharded.argtypes = [vp, u64, vp, vp, vp, vp, vp, i32, u32, vp, vp, vp, vp]
     L.ss_index_set_doc_base.argtypes = [vp, u64]
+    L.ss_topics_load.argtypes = [vp, u64, u32, vp, vp, vp, vp]
+    L.ss_topic_probs.argtypes = [vp, u64, vp, vp, vp]
     L.ss_merge_topk.argtypes = [vp, u32, u64, u32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ss_score_get_stats.argtypes = [vp, C.POINTER(ScoreStats)]
     for name in EXPORTS:
@@ -265,6 +267,21 @@ class Engine:
         fn = self.L.ss_score_batch_sharded if sharded else self.L.ss_score_batch
         self._check(fn(self.h, nq, _ptr(kw_ptr), _ptr(kw_terms), _ptr(ph_ptr), _ptr(ph_terms),
                 _ptr(topic_probs), per_q, k, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3])))
+        return out
+
+    def topics_load(self, term_ptr, topic_ids, freq, word_count):
+        """inv[2] as CSR (term -> (topic id, frequency)) + forw[5] wordCount per topic (extension, 8(f)-3)."""
+        term_ptr, topic_ids = _as(term_ptr, np.uint64), _as(topic_ids, np.uint32)
+        freq, word_count = _as(freq, np.float64), _as(word_count, np.float64)
+        self._check(self.L.ss_topics_load(self.h, len(term_ptr) - 1, len(word_count), _ptr(term_ptr), _ptr(topic_ids),
+                                          _ptr(freq), _ptr(word_count)))
+        self._n_topics_nb = len(word_count)
+
+    def topic_probs(self, tok_ptr, tok_terms):
+        """-> [Q][T] naive-Bayes topic probabilities of the queries' keyword tokens."""
+        tok_ptr, tok_terms = _as(tok_ptr, np.uint64), _as(tok_terms, np.uint32)
+        out = np.zeros((len(tok_ptr) - 1, self._n_topics_nb), dtype=np.float64)
+        self._check(self.L.ss_topic_probs(self.h, len(tok_ptr) - 1, _ptr(tok_ptr), _ptr(tok_terms), _ptr(out)))
         return out
 
     def merge_topk(self, docs, finals, prs, counts):

@@ -28,6 +28,16 @@ struct TableState {
   }
 };
 
+// inv[2] (word -> {topic: frequency}) and forw[5]'s wordCount column, for ss_topic_probs (topics.cu)
+struct TopicTable {
+  bool loaded = false;
+  uint64_t n_terms = 0;
+  uint32_t T = 0;
+  ss::DevBuf<uint64_t> term_ptr;
+  ss::DevBuf<uint32_t> topic_ids;
+  ss::DevBuf<double> freq, word_count;
+};
+
 struct IndexState {
   uint64_t D = 0;  // doc id space (shard-local ids 0 .. D-1)
   uint64_t doc_base = 0;  // global id of local doc 0 (doc-sharded index): added to the ids ss_score_batch returns
@@ -58,6 +68,7 @@ struct IndexState {
   ss::DevBuf<uint8_t> dense_map;  // [V] dense slot of a term, 255 = none
   uint64_t dense_map_V = 0;
   std::vector<uint8_t> dense_host;  // [dense_map_V] 1 = the term has an impact vector (host copy for the byte model)
+  TopicTable topics;
   ss_score_stats stats{};
   // grow-only device workspace of ss_score_batch (cudaMalloc/cudaFree per batch would
   // synchronise the device and dominate small batches)

@@ -1073,6 +1073,8 @@ struct PagerankState {
   std::vector<uint32_t> chunk_rows, chunk_task, chunk_fix;  // [n_chunks + 1] local row / task / fix-row boundaries
   std::vector<uint64_t> all_chunk_rows;                     // [world][n_chunks + 1] global row boundaries of every rank
   cudaStream_t xstream = nullptr;                           // exchange stream (NCCL calls of the sweep loop)
+  cudaStream_t pstream[kMaxPeers] = {};                     // one copy stream per peer: the peer copies of a chunk run
+  cudaEvent_t pdone[kMaxPeers] = {};                        // on different copy engines at the same time
   cudaEvent_t chunk_ev[8] = {}, x_done = nullptr, red_done = nullptr;
   cudaEvent_t x_t0 = nullptr, x_t1 = nullptr;               // timing: exchange stream busy interval of a sweep
   // per-run state
@@ -1088,8 +1090,13 @@ struct PagerankState {
   ss_pagerank_stats stats{};
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [4]: end of the short-row kernel
   cudaEvent_t out_ev[2] = {nullptr, nullptr};
-  // fused exchange over peer memory (CUDA IPC): peers' y[0]/y[1]
+  // exchange over peer memory (CUDA IPC): peers' y[0]/y[1] mapped into this process.
+  //   fused: the peers are mapped (every rank agreed);  push_from_epilogue: 2 ranks, the sweep epilogue stores
+  //   each finished row into the peer's state;  otherwise (3+ ranks) finished row chunks are pushed to every
+  //   peer with copy-engine peer copies on the exchange stream, overlapped with the next chunk's sweep.
   bool fused = false;
+  bool push_from_epilogue = false;
+  int peer_rank[kMaxPeers] = {};
   int n_peers = 0;
   double* peer_y[2][kMaxPeers] = {};
   void* y_base_exported[2] = {nullptr, nullptr};
@@ -1127,9 +1134,13 @@ static int open_peers(ss_engine* e, PagerankState* s) {
   // for free (2 GPUs: 658 -> 870 GTEPS), but seven 128-byte remote stores per row throttle the
   // whole sweep (70 ms vs 5 ms + 14.5 ms NCCL).  Default: fused for 2 ranks, NCCL beyond;
   // SS_PR_EXCHANGE=fused|nccl overrides.
+  // Round 2: with 3+ ranks the rows no longer leave from the epilogue; finished chunks are pushed by the copy
+  // engines instead (see PagerankState::fused), which costs the sweep no issue slots at all.
+  // SS_PR_EXCHANGE=nccl keeps everything on NCCL broadcasts; =fused forces the epilogue push, =copy the
+  // copy-engine push, at any rank count.
   const char* env = getenv("SS_PR_EXCHANGE");
   if (env && !strcmp(env, "nccl")) return SS_OK;
-  if (world > 2 && !(env && !strcmp(env, "fused"))) return SS_OK;
+  s->push_from_epilogue = (world == 2 && !(env && !strcmp(env, "copy"))) || (env && !strcmp(env, "fused"));
   struct Pack {
     cudaIpcMemHandle_t h[2];
     int device;
@@ -1151,6 +1162,7 @@ static int open_peers(ss_engine* e, PagerankState* s) {
       }
       s->peer_y[b][q] = (double*)ptr;
     }
+    s->peer_rank[q] = r;
     ++q;
   }
   s->n_peers = q;
@@ -1192,6 +1204,10 @@ void pagerank_state_free(PagerankState* s) {
   if (s->x_t0) cudaEventDestroy(s->x_t0);
   if (s->x_t1) cudaEventDestroy(s->x_t1);
   if (s->xstream) cudaStreamDestroy(s->xstream);
+  for (auto& st : s->pstream)
+    if (st) cudaStreamDestroy(st);
+  for (auto& ev : s->pdone)
+    if (ev) cudaEventDestroy(ev);
   delete s;
 }
 
@@ -1235,6 +1251,8 @@ static int create_sync_objects(PagerankState* s) {
   SS_CUDA(cudaEventCreate(&s->x_t0));
   SS_CUDA(cudaEventCreate(&s->x_t1));
   SS_CUDA(cudaStreamCreateWithFlags(&s->xstream, cudaStreamNonBlocking));
+  for (auto& st : s->pstream) SS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  for (auto& ev : s->pdone) SS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   return SS_OK;
 }
 
@@ -1855,10 +1873,11 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
     p.active_mask = active;
     p.tele = tele;
     p.first = sweep == 1;
-    p.n_peers = s->fused ? s->n_peers : 0;
-    for (int q = 0; q < kMaxPeers; ++q) p.peer_next[q] = s->fused ? s->peer_y[s->cur ^ 1][q] : nullptr;
+    const bool epi_push = s->fused && s->push_from_epilogue;
+    p.n_peers = epi_push ? s->n_peers : 0;
+    for (int q = 0; q < kMaxPeers; ++q) p.peer_next[q] = epi_push ? s->peer_y[s->cur ^ 1][q] : nullptr;
     if (timing) SS_CUDA(cudaEventRecord(s->ev[0], st));
-    const bool overlap = world > 1 && !s->fused;  // NCCL exchange on its own stream, chunk by chunk
+    const bool overlap = world > 1 && !epi_push;  // exchange on its own stream, chunk by chunk
     for (int c = 0; c < C; ++c) {
       const ChunkShape& k = chunks[c];
       rc = dispatch_shape(shape, [&](auto lpr, auto vec) {
@@ -1904,7 +1923,22 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
         SS_CUDA(cudaStreamWaitEvent(s->xstream, s->chunk_ev[c], 0));
         if (timing && c == 0) SS_CUDA(cudaEventRecord(s->x_t0, s->xstream));
         chunk_bytes(c);
-        SS_TRY(comm_allgatherv_bytes_on(e, s->xstream, p.y_next, byte_off.data(), byte_cnt.data()));
+        if (s->fused) {
+          // copy-engine push: my chunk into every peer's copy of the state, starting with a different peer
+          // on every rank so that the receivers' links fill evenly
+          const int rank = comm_rank(e);
+          for (int i = 0; i < s->n_peers && byte_cnt[rank]; ++i) {
+            int q = 0;
+            for (int j = 0; j < s->n_peers; ++j)
+              if (s->peer_rank[j] == (rank + 1 + i) % world) q = j;
+            char* dst = reinterpret_cast<char*>(s->peer_y[s->cur ^ 1][q]) + byte_off[rank];
+            const char* src = reinterpret_cast<const char*>(p.y_next) + byte_off[rank];
+            SS_CUDA(cudaStreamWaitEvent(s->pstream[i], s->chunk_ev[c], 0));
+            SS_CUDA(cudaMemcpyAsync(dst, src, byte_cnt[rank], cudaMemcpyDefault, s->pstream[i]));
+          }
+        } else {
+          SS_TRY(comm_allgatherv_bytes_on(e, s->xstream, p.y_next, byte_off.data(), byte_cnt.data()));
+        }
       }
     }
     k_reduce_partials<<<kReduceCtas, kThreads, 0, st>>>(s->red.p, sweep_slots, W, s->stage.p);
@@ -1916,6 +1950,11 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
       // every rank's pushed rows before anybody's next sweep)
       SS_CUDA(cudaEventRecord(s->red_done, st));
       SS_CUDA(cudaStreamWaitEvent(s->xstream, s->red_done, 0));
+      if (overlap && s->fused)  // the peer copies of every chunk precede the all-reduce
+        for (int i = 0; i < s->n_peers; ++i) {
+          SS_CUDA(cudaEventRecord(s->pdone[i], s->pstream[i]));
+          SS_CUDA(cudaStreamWaitEvent(s->xstream, s->pdone[i], 0));
+        }
       if (timing && !overlap) SS_CUDA(cudaEventRecord(s->x_t0, s->xstream));
       SS_TRY(comm_allreduce_sum_f64_on(e, s->xstream, s->sums.p, W));
       if (timing) SS_CUDA(cudaEventRecord(s->x_t1, s->xstream));

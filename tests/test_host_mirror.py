@@ -189,3 +189,13 @@ def test_go_api_over_snapshots(engine, tmp_path):
             assert batched[i] == db.retrieve(engine, qs[i][0], qs[i][1])
     finally:
         db.close()
+
+
+@pytest.mark.gpu
+def test_c1_at_size(engine, tmp_path):
+    """BASELINE.json configs[0] at its stated size through the reference's table encodings."""
+    from tests import c1_workload as c1
+    w = c1.make_tables(tmp_path)
+    results, times = c1.run(engine, tmp_path, w)
+    info = c1.check(tmp_path, w, results)
+    assert info["queries"] == 100 and info["results_compared"] > 0

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import loader as O
-from spaghettisearch_b200 import synth
+from spaghettisearch_b200 import capi, synth
 
 pytestmark = pytest.mark.gpu
 KATS = json.loads((Path(__file__).parent / "golden" / "kats.json").read_text())

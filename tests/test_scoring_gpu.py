@@ -398,3 +398,39 @@ def test_reload_with_more_docs_refreshes_blend_cache(engine):
         exp = O.score_batch(tabs[0][0], tabs[1][0], D, tabs[0][1], tabs[1][1], pr, q.kw_ptr, q.kw_terms,
                             topic_probs=probs, k=10)
         assert_same_results(got, exp)
+
+
+def test_live_topic_probabilities_extension(engine):
+    """SURVEY.md 8(f)-3 (opt-in, beyond the shipped reference): the repaired computeTopicProbs feeding the
+    PageRank blend per query.  ss_topic_probs is bit-exact against the oracle's restatement, and a batch scored
+    with those per-query vectors matches the oracle end to end."""
+    rng = np.random.default_rng(21)
+    n_words, T = 500, 8
+    rows = [sorted(rng.choice(T, size=int(rng.integers(0, 5)), replace=False)) for _ in range(n_words)]
+    term_ptr = np.zeros(n_words + 1, np.uint64)
+    term_ptr[1:] = np.cumsum([len(r) for r in rows])
+    topic_ids = np.array([t for r in rows for t in r], np.uint32)
+    freq = rng.integers(1, 50, len(topic_ids)).astype(np.float64)   # inv[2] stores counts (uint32)
+    word_count = rng.integers(1000, 5000, T).astype(np.float64)     # forw[5] "wordCount"
+    engine.topics_load(term_ptr, topic_ids, freq, word_count)
+    V, D = 300, 3000
+    tabs = _small_index(engine, V, D)
+    q = synth.queries(300, V, phrase_fraction=0.2, seed=12)
+    # the query tokens' ids in inv[2]'s word space: here the same numbering, one token unknown to inv[2]
+    tok = q.kw_terms.copy()
+    tok[::17] = 100000
+    got = engine.topic_probs(q.kw_ptr, tok)
+    exp = O.topic_probs(term_ptr, topic_ids, freq, word_count, q.kw_ptr, tok)
+    assert np.array_equal(got, exp) and (got > 0).any() and (got == 0).any()
+    # one-token query listing topic t: exactly freq / wordCount / T (computed like Go: (1 * f/wc) / T)
+    w = next(i for i, r in enumerate(rows) if len(r))
+    one = engine.topic_probs([0, 1], [w])
+    x = int(term_ptr[w])
+    assert one[0, topic_ids[x]] == (1.0 * (freq[x] / word_count[topic_ids[x]])) / T
+    pr = rng.random((D, T)) * 1e-2
+    engine.set_pagerank(pr)
+    res = engine.score_batch(q.kw_ptr, q.kw_terms, q.ph_ptr, q.ph_terms, topic_probs=got * 1e4, k=10)
+    ref = O.score_batch(tabs[0][0], tabs[1][0], D, tabs[0][1], tabs[1][1], pr, q.kw_ptr, q.kw_terms, q.ph_ptr,
+                        q.ph_terms, topic_probs=exp * 1e4, k=10)
+    assert_same_results(res, ref)
+    assert (res[2] != 0).any()  # the blend really is live
