@@ -133,15 +133,16 @@ def pin_view(t, dtype):
 
 # --------------------------------------------------------------------------- ours
 def pr_grid(world, spec):
-    """(row groups, topic groups) of the PageRank engine grid.  A GPU gathers ~40-45 G source rows/s whatever
+    """(row groups, topic groups) of the PageRank engine grid.  A GPU gathers ~36-45 G source rows/s whatever
     the row width (scripts/bench_gather2.cu), so splitting the 16 topics across GPUs halves a GPU's
     topic-edge rate per split; splitting rows costs an exchange of the replicated state that grows with the
-    group.  Up to 4 GPUs the (overlapped) exchange is cheaper; at 8 a 4 x 2 grid halves it."""
+    row group and moves at ~460 GB/s per GPU and direction when every GPU sends and receives at once.
+    Measured (profiles/r02_multigpu.txt): 4 GPUs 4x1 924 / 2x2 1027 GTEPS; 8 GPUs 8x1 683 / 4x2 1586 / 2x4 1189."""
     if spec:
         rg, tg = (int(x) for x in spec.lower().split("x"))
         assert rg * tg == world and T_TOPICS % tg == 0, spec
         return rg, tg
-    return {1: (1, 1), 2: (2, 1), 4: (4, 1), 8: (4, 2)}.get(world, (world, 1))
+    return {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}.get(world, (world, 1))
 
 
 def run_c1(args):
@@ -571,7 +572,7 @@ def run_scoring(args, ctx):
                      "traffic": ncu_traffic("score_dram_bytes") if world == 1 else None, "peak_source": peak_src,
                      "kernel": "k_score",
                      "bytes_model": "what the default path has to move: a query with a dense keyword streams 2 B per "
-                                    "doc for each of its dense tokens and for the blend bound, and reads 8 B per "
+                                    "doc for each of its dense tokens and reads 8 B per "
                                     "posting of its other tokens; any other query reads 8 B per posting of every "
                                     "list; + 12 B per result.  Survivor lookups are not counted.",
                      "model_bytes_per_batch": a["model_bytes"] // max(1, args.steps),

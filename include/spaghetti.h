@@ -231,7 +231,7 @@ typedef struct ss_score_stats {
   double shard_merge_ms;       /* device time from the end of the local merge to the end of the result copies
                                   (ss_score_batch_sharded: NCCL all-gather + cross-shard merge + D2H) */
   uint64_t model_bytes;        /* bytes the batch has to move on the path it takes: a query with a dense keyword
-                                  streams 2 B per doc per dense token (+ the blend bound) and reads 8 B per posting
+                                  streams 2 B per doc per dense token and reads 8 B per posting
                                   of its other tokens; other queries read 8 B per posting; + 12 B per result */
 } ss_score_stats;
 SS_API int ss_score_get_stats(ss_engine* e, ss_score_stats* out);

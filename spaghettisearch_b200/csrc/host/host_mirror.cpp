@@ -567,6 +567,12 @@ BatchingRetriever::~BatchingRetriever() {
 }
 std::vector<Rank_combined> BatchingRetriever::Submit(const std::vector<std::string>& queryTokenised,
                                                      const std::vector<std::string>& phraseTokenised) {
+  // The engine serves up to 256 keyword tokens per query (a longer phrase is simply never a hit, as in the
+  // reference); a request beyond that fails HERE, for its own caller only, instead of failing the whole
+  // coalesced batch for everybody who happened to share the window.
+  if (queryTokenised.size() > 256)
+    throw std::runtime_error("Retrieve: " + std::to_string(queryTokenised.size()) +
+                             " keyword tokens in one query (the engine serves up to 256)");
   std::future<std::vector<Rank_combined>> fut;
   {
     std::lock_guard<std::mutex> lock(impl_->mu);

@@ -1786,29 +1786,43 @@ SS_API int ss_pagerank(ss_engine* e, double damping, double eps, uint32_t n_topi
   const uint32_t red_slots = std::max(sweep_slots, grid_init);
   const int W = 3 * TP;
 
-  if (world > 1) {  // fixed-size state so that the peer mappings survive topic-count changes
-    SS_TRY(s->y[0].reserve(N * 16));
-    SS_TRY(s->y[1].reserve(N * 16));
+  // Every allocation of the run happens here, before the first collective, and the ranks agree on the outcome:
+  // a rank that runs out of memory makes all of them return instead of leaving the others inside NCCL
+  // (ADVICE round 1).
+  auto allocate = [&]() -> int {
+    // multi-rank: fixed-size state so that the peer mappings survive topic-count changes
+    SS_TRY(s->y[0].reserve(world > 1 ? N * 16 : N * TP));
+    SS_TRY(s->y[1].reserve(world > 1 ? N * 16 : N * TP));
+    SS_TRY(s->mul.reserve(R));
+    SS_TRY(s->mul2.reserve(R));
+    SS_TRY(s->partials.reserve((size_t)s->n_tasks * TP));
+    SS_TRY(s->red.reserve((size_t)red_slots * W));
+    SS_TRY(s->sums.reserve(W));
+    SS_TRY(s->stage.reserve((size_t)kReduceCtas * W));
+    SS_TRY(s->tot.reserve(TP));
+    SS_TRY(s->init.reserve(TP));
+    if (s->tele_T) SS_TRY(s->tele_w.reserve((size_t)R * TP));
+    return SS_OK;
+  };
+  const int64_t alloc_status = allocate();
+  if (world > 1) {
+    int64_t all_status[64];
+    SS_TRY(comm_allgather_host_bytes(e, &alloc_status, sizeof(alloc_status), all_status));
+    for (int r = 0; r < world; ++r)
+      if (all_status[r] < 0) {
+        if (alloc_status >= 0) ss::set_error("ss_pagerank: rank %d could not allocate its state", r);
+        return alloc_status < 0 ? (int)alloc_status : SS_ERR_OOM;
+      }
     SS_TRY(open_peers(e, s));
     SS_TRY(agree_on_fused(e, s));
-  } else {
-    SS_TRY(s->y[0].reserve(N * TP));
-    SS_TRY(s->y[1].reserve(N * TP));
+  } else if (alloc_status < 0) {
+    return (int)alloc_status;
   }
-  SS_TRY(s->mul.reserve(R));
-  SS_TRY(s->mul2.reserve(R));
-  SS_TRY(s->partials.reserve((size_t)s->n_tasks * TP));
-  SS_TRY(s->red.reserve((size_t)red_slots * W));
-  SS_TRY(s->sums.reserve(W));
-  SS_TRY(s->stage.reserve((size_t)kReduceCtas * W));
-  SS_TRY(s->tot.reserve(TP));
-  SS_TRY(s->init.reserve(TP));
 
   const bool biased = s->tele_T != 0;
   if (biased) {
     SS_REQUIRE(s->tele_T == n_topics, SS_ERR_INVALID, "ss_pagerank: teleport weights were set for %u topics, run has %u",
                s->tele_T, n_topics);
-    SS_TRY(s->tele_w.reserve((size_t)R * TP));
     if (R) k_pad_rows<<<ss::div_up((uint64_t)R * TP, 256), 256, 0, st>>>(s->tele_raw.p, R, T, TP, s->tele_w.p);
   }
   double h_init[16];

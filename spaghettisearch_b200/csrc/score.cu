@@ -782,8 +782,9 @@ static int score_batch_core(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, 
   SS_CUDA(cudaMemcpyAsync(h_stats, ws.stats.p, 16, cudaMemcpyDeviceToHost, st));
   if (timing) SS_CUDA(cudaEventRecord(ws.ev[3], st));
   // Byte model of what this batch has to move on the path it takes (host arithmetic while the kernels run):
-  // a query with a dense keyword streams 2 B per doc for each dense token and for the blend bound and reads
-  // 8 B per posting of its other tokens; any other query reads 8 B per posting of all its lists.
+  // a query with a dense keyword streams 2 B per doc for each of its dense tokens (the blend bound is only read
+  // for the few 8-doc groups that pass the first test) and reads 8 B per posting of its other tokens; any other
+  // query reads 8 B per posting of all its lists.
   uint64_t model_bytes = 12ull * k * n_q;
   {
     const bool dense_on = use_dense && ix->dense_valid && ix->n_dense && !ix->dense_host.empty();
@@ -809,7 +810,7 @@ static int score_batch_core(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, 
       for (uint64_t i = kw_ptr[q]; i < kw_ptr[q + 1]; ++i) visit(kw_terms[i], true);
       if (ph_ptr)
         for (uint64_t i = ph_ptr[q]; i < ph_ptr[q + 1]; ++i) visit(ph_terms[i], false);
-      model_bytes += dense_kw ? 2ull * D * (n_dense_tok + 1) + 8ull * sparse_postings : 8ull * all_postings;
+      model_bytes += dense_kw ? 2ull * D * n_dense_tok + 8ull * sparse_postings : 8ull * all_postings;
     }
   }
   ix->stats.model_bytes = model_bytes;
