@@ -148,7 +148,7 @@ SS_API int ss_index_load(ss_engine* e, int table, uint64_t n_terms, uint64_t n_d
  * size only.  Default 0. */
 SS_API int ss_index_set_doc_base(ss_engine* e, uint64_t doc_base);
 
-/* Drop both tables, their norms and the blend input (before loading another index). */
+/* Drop both tables, their norms, the blend input and the topic table (before loading another index). */
 SS_API int ss_index_clear(ss_engine* e);
 
 /* idf = float32(log2(total_docs / df)) with Go's Log2, w = norm_tf * idf in

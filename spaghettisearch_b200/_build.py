@@ -63,7 +63,8 @@ def build_synth(force: bool = False, verbose: bool = False) -> Path:
 
 def gpu_sources():
     cu = sorted(CSRC.glob("*.cu"))
-    hdr = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "spaghetti.h"]
+    hdr = (sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.inc")) +
+           [ROOT / "include" / "spaghetti.h"])
     return cu, hdr
 
 

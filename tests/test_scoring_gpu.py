@@ -412,9 +412,9 @@ def test_live_topic_probabilities_extension(engine):
     topic_ids = np.array([t for r in rows for t in r], np.uint32)
     freq = rng.integers(1, 50, len(topic_ids)).astype(np.float64)   # inv[2] stores counts (uint32)
     word_count = rng.integers(1000, 5000, T).astype(np.float64)     # forw[5] "wordCount"
-    engine.topics_load(term_ptr, topic_ids, freq, word_count)
     V, D = 300, 3000
-    tabs = _small_index(engine, V, D)
+    tabs = _small_index(engine, V, D)  # (ss_index_clear drops a topic table too: load it afterwards)
+    engine.topics_load(term_ptr, topic_ids, freq, word_count)
     q = synth.queries(300, V, phrase_fraction=0.2, seed=12)
     # the query tokens' ids in inv[2]'s word space: here the same numbering, one token unknown to inv[2]
     tok = q.kw_terms.copy()
