@@ -160,7 +160,7 @@ def run_c1(args):
         results, times = c1.run(eng, tmp, w)
         info = c1.check(tmp, w, results)
     eng.close()
-    total = sum(v for k, v in times.items() if k != "load_snapshots")
+    total = sum(v for k, v in times.items() if k not in ("load_snapshots", "score_batch_calls"))
     cpu_total = sum(info["cpu_seconds"].values())
     print(json.dumps({
         "metric": "c1_go_api_seconds", "value": total, "unit": "s", "n_gpus": 1, "steps": 1, "warmup": 1,
@@ -589,6 +589,18 @@ def run_scoring(args, ctx):
     }
     if parity is not None:
         sc["parity"] = parity
+    # single-query latency through the same entry point (retrieval.Retrieve is called once per HTTP request,
+    # cmd/server/server.go:47): wall clock of 200 one-query calls, index resident
+    lat = []
+    for i in range(200):
+        a0, a1 = int(q.kw_ptr[i]), int(q.kw_ptr[i + 1])
+        one_ptr, one_kw = np.array([0, a1 - a0], np.uint64), np.ascontiguousarray(q.kw_terms[a0:a1])
+        t0 = time.perf_counter()
+        eng.score_batch(one_ptr, one_kw, topic_probs=probs, k=TOP_K, sharded=True)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lat.sort()
+    sc["single_query_latency_ms"] = {"p50": lat[len(lat) // 2], "p90": lat[int(len(lat) * 0.9)], "max": lat[-1],
+                                     "what": "one ss_score_batch_sharded call per query, first 200 queries of the batch"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_scoring(eng, title, body, D, q, probs, cores)

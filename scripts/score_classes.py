@@ -36,11 +36,27 @@ def run(idx):
     for _ in range(2):
         e.score_batch(ptr, kw, topic_probs=probs, k=10); s = e.score_stats()
     return s
-s_all = run(list(range(Q)))
-print(f"whole batch: {s_all.kernel_ms:.1f} ms ({Q / s_all.kernel_ms * 1e3:.0f} q/s), k_score {s_all.score_kernel_ms:.1f} ms")
-tot = 0.0
-for c, idx in sorted(classes.items()):
-    s = run(idx); tot += s.score_kernel_ms
-    print(f"{c:28s} {len(idx):6d} queries  k_score {s.score_kernel_ms:8.2f} ms  {s.score_kernel_ms * 1e3 / len(idx):7.2f} us/query  "
-          f"model GB {s.model_bytes / 1e9:8.1f}  -> {s.model_bytes / s.score_kernel_ms / 1e6:6.0f} GB/s", flush=True)
-print(f"sum of classes {tot:.1f} ms")
+import os
+configs = [("block maxima off, slab-kth bound", {"SS_SCORE_BLOCKMAX": "0", "SS_SCORE_GTOP": "0"}),
+           ("block maxima on,  slab-kth bound", {"SS_SCORE_BLOCKMAX": "1", "SS_SCORE_GTOP": "0"}),
+           ("block maxima on,  global top-k bound (default)", {})]
+ref = None
+for name, env in configs:
+    os.environ.update(env)
+    print("==", name, flush=True)
+    ptr0 = np.asarray(q.kw_ptr, np.uint64)
+    for _ in range(2):
+        res = e.score_batch(ptr0, kt, topic_probs=probs, k=10); s_all = e.score_stats()
+    if ref is None:
+        ref = [r.copy() for r in res]
+    else:
+        assert all(np.array_equal(a, b) for a, b in zip(ref, res)), "results differ between configurations"
+    print(f"whole batch: {s_all.kernel_ms:.1f} ms ({Q / s_all.kernel_ms * 1e3:.0f} q/s), k_score {s_all.score_kernel_ms:.1f} ms", flush=True)
+    tot = 0.0
+    for c, idx in sorted(classes.items()):
+        s = run(idx); tot += s.score_kernel_ms
+        print(f"{c:28s} {len(idx):6d} queries  k_score {s.score_kernel_ms:8.2f} ms  {s.score_kernel_ms * 1e3 / len(idx):7.2f} us/query  "
+              f"model GB {s.model_bytes / 1e9:8.1f}  -> {s.model_bytes / s.score_kernel_ms / 1e6:6.0f} GB/s", flush=True)
+    print(f"sum of classes {tot:.1f} ms")
+    for k_ in env:
+        del os.environ[k_]

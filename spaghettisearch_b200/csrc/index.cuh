@@ -63,6 +63,7 @@ struct IndexState {
   uint32_t n_dense = 0;
   uint64_t d_pad = 0;           // padded doc count of one vector
   ss::DevBuf<uint16_t> uvec;    // [n_dense][d_pad] fp16 bits
+  ss::DevBuf<float2> ublk;      // [n_dense][d_pad / 4096] {largest impact, postings} per block of a vector
   ss::DevBuf<uint16_t> zvec;    // [d_pad]
   ss::DevBuf<float> zblk;       // [d_pad / 4096] largest blend term per doc block
   ss::DevBuf<uint8_t> dense_map;  // [V] dense slot of a term, 255 = none
@@ -76,7 +77,8 @@ struct IndexState {
     ss::DevBuf<uint64_t> kw_ptr, ph_ptr;
     ss::DevBuf<uint32_t> kw, ph, part_doc, part_count, out_doc, out_count, narrow;
     ss::DevBuf<double> probs, part_final, part_pr, out_final, out_pr, zero_mag;
-    ss::DevBuf<unsigned long long> stats, qthr;
+    ss::DevBuf<unsigned long long> stats, qthr, gtop;
+    ss::DevBuf<uint32_t> glock;
     ss::DevBuf<uint8_t> group_len;
     // cross-shard gather of ss_score_batch_sharded: [world][n_q][k] lists and [world][n_q] counts
     ss::DevBuf<uint32_t> all_doc, all_count, loc_doc, loc_count;

@@ -75,12 +75,18 @@ struct ScoreParams {
   unsigned long long* stats;  // [0] postings scanned, [1] docs matched
   unsigned long long* qthr;   // [n_q] running per-query bound (score key), zeroed per batch
   int use_qthr;
+  unsigned long long* gtop;   // [n_q][k] the k best keys of the slabs finished so far (k <= 32), or NULL
+  uint32_t* glock;            // [n_q] lock of gtop[q]
   // impact vectors of the densest terms (see IndexState)
   const uint16_t* uvec;       // [n_dense][d_pad] fp16 bits, NULL = path disabled
   const uint16_t* zvec;       // [d_pad]
   const float* zblk;          // [d_pad / kRange] largest blend term of a doc block
   const uint8_t* dense_map;   // [dense_map_V]
   uint64_t d_pad, dense_map_V;
+  // block maxima of the impact vectors: ublk[slot][block] = {largest impact, number of postings} of the
+  // kDenseRange-doc block, NULL = no block skipping (SS_SCORE_BLOCKMAX=0 or slabs not block aligned)
+  const float2* ublk;
+  uint32_t n_blk;
   // slab groups (k_plan): group_len[q][slab] = number of consecutive slabs the CTA of (q, slab) scores as
   // one range, 0 = the slab belongs to an earlier CTA's group (that CTA exits at once)
   const uint8_t* group_len;
@@ -400,6 +406,36 @@ __global__ void k_dense_fill(TableView tv, int table, const uint32_t* __restrict
     u[doc] = h;
   }
 }
+// {largest impact, number of postings} of every kDenseRange-doc block of every impact vector
+// (grid: blocks x dense slots): what lets the stream skip a block it cannot find a candidate in
+__global__ void k_dense_blk(const uint16_t* __restrict__ uvec, uint64_t d_pad, uint32_t n_blk, float2* __restrict__ ublk) {
+  __shared__ float smax[256 / 32];
+  __shared__ uint32_t scnt[256 / 32];
+  const uint16_t* u = uvec + (size_t)blockIdx.y * d_pad + (size_t)blockIdx.x * kDenseRange;
+  float m = 0.0f;
+  uint32_t c = 0;
+  for (uint32_t i = threadIdx.x; i < (uint32_t)kDenseRange; i += blockDim.x) {
+    const uint16_t h = u[i];
+    c += h != 0;
+    m = fmaxf(m, __half2float(__ushort_as_half(h)));  // impacts are >= 0, never NaN (k_dense_fill)
+  }
+  for (int o = 16; o; o >>= 1) {
+    m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    smax[threadIdx.x >> 5] = m;
+    scnt[threadIdx.x >> 5] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 256 / 32; ++w) {
+      m = fmaxf(m, smax[w]);
+      c += scnt[w];
+    }
+    ublk[(size_t)blockIdx.y * n_blk + blockIdx.x] = make_float2(m, (float)c);
+  }
+}
 // largest 33 * blend input of every kRange-doc block (one CTA per block)
 __global__ void k_zblk(const float4* __restrict__ meta32, uint64_t D, float* __restrict__ zblk) {
   __shared__ float sm[256];
@@ -499,9 +535,12 @@ static int build_dense_vectors(ss_engine* e, IndexState* ix, cudaStream_t st, ui
         for (int tb = 1; tb >= 0; --tb)
           if (ix->tab[tb].loaded)
             k_dense_fill<<<grid, 256, 0, st>>>(view_of(ix->tab[tb]), tb, d_term.p, ix->meta32.p, d_pad, ix->uvec.p);
+        const uint32_t n_blk = (uint32_t)(d_pad / kDenseRange);
+        SS_TRY(ws_reserve(ix->ublk, (size_t)nd * n_blk));
+        k_dense_blk<<<dim3(n_blk, nd), 256, 0, st>>>(ix->uvec.p, d_pad, n_blk, ix->ublk.p);
         SS_CUDA(cudaStreamSynchronize(st));  // d_term goes out of scope
         SS_CUDA(cudaGetLastError());
-        *launches += 4;
+        *launches += 5;
       }
       ix->n_dense = nd;
       ix->dense_map_V = V;
@@ -603,6 +642,8 @@ static int score_batch_core(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, 
   SS_TRY(ws_reserve(ws.out_count, n_q));
   SS_TRY(ws_reserve(ws.stats, 2));
   SS_TRY(ws_reserve(ws.qthr, n_q));
+  SS_TRY(ws_reserve(ws.gtop, n_q * std::min<uint32_t>(k, 32)));
+  SS_TRY(ws_reserve(ws.glock, n_q));
   if (world > 1) {
     SS_TRY(ws_reserve(ws.all_doc, (size_t)world * n_q * k));
     SS_TRY(ws_reserve(ws.all_final, (size_t)world * n_q * k));
@@ -650,6 +691,12 @@ static int score_batch_core(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, 
   }
   SS_CUDA(cudaMemsetAsync(ws.stats.p, 0, 16, st));
   SS_CUDA(cudaMemsetAsync(ws.qthr.p, 0, n_q * 8, st));
+  bool global_topk = k <= 32;
+  if (const char* env = getenv("SS_SCORE_GTOP")) global_topk = global_topk && atoi(env) != 0;
+  if (global_topk) {
+    SS_CUDA(cudaMemsetAsync(ws.gtop.p, 0, n_q * k * 8, st));
+    SS_CUDA(cudaMemsetAsync(ws.glock.p, 0, n_q * 4, st));
+  }
   // blend term: one pass over forw[3] for a shared topic vector, cached across batches
   const double* sqd_ptr = nullptr;
   if (shared_blend) {
@@ -725,9 +772,19 @@ static int score_batch_core(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, 
     p.dense_map = ix->dense_map.p;
     p.d_pad = ix->d_pad;
     p.dense_map_V = ix->dense_map_V;
+    bool block_max = true;
+    if (const char* env = getenv("SS_SCORE_BLOCKMAX")) block_max = atoi(env) != 0;
+    if (block_max && (sub_per_slab * kRange) % kDenseRange == 0) {  // slab starts are block boundaries
+      p.ublk = ix->ublk.p;
+      p.n_blk = (uint32_t)(ix->d_pad / kDenseRange);
+    }
   }
   p.use_qthr = 1;
   if (const char* env = getenv("SS_SCORE_QTHR")) p.use_qthr = atoi(env);
+  if (global_topk && p.use_qthr) {
+    p.gtop = ws.gtop.p;
+    p.glock = ws.glock.p;
+  }
 
   p.narrow = ws.narrow.p;
   p.prefetch_meta = 0;  // measured: no effect (the finalize step is issue bound, not latency bound)
