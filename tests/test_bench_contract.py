@@ -34,3 +34,32 @@ def test_reference_arm_other_ranks_do_nothing(built):
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "1"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_pagerank_grid_policy():
+    """bench.py's row x topic engine grid: covers the world, topic groups divide the 16 topics."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    for world in (1, 2, 4, 8):
+        rg, tg = bench.pr_grid(world, "")
+        assert rg * tg == world and bench.T_TOPICS % tg == 0
+    assert bench.pr_grid(8, "2x4") == (2, 4) and bench.pr_grid(1, "") == (1, 1)
+
+
+def test_go_shim_files_reference_only_declared_entry_points():
+    """integration/go/gpuengine/engine.go is the only cgo file; every C.ss_* it calls is declared in spaghetti.h."""
+    import re
+    header = (ROOT / "include" / "spaghetti.h").read_text()
+    declared = set(re.findall(r"SS_API\s+[\w\s\*]+?\b(ss_\w+)\s*\(", header))
+    go_dir = ROOT / "integration" / "go"
+    used = set()
+    for f in go_dir.rglob("*.go"):
+        text = f.read_text()
+        calls = set(re.findall(r"C\.(ss_\w+)\(", text))
+        if f.name != "engine.go":
+            assert 'import "C"' not in text and not calls, f
+        used |= calls
+    assert used and used <= declared, used - declared
+    for name in ("ss_create", "ss_graph_load_csr", "ss_pagerank", "ss_index_load", "ss_term_weights", "ss_set_doc_norms",
+                 "ss_set_pagerank", "ss_score_batch"):
+        assert name in used, name
