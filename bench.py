@@ -37,6 +37,21 @@ EPS = 1e-9       # BASELINE.json configs[1]
 TOP_K = 10       # BASELINE.json configs[2]
 
 
+def pagerank_workload(args, strong=False):
+    return ("BASELINE.json configs[1]: topic-sensitive PageRank, 16 ODP topics, "
+            f"{args.nodes} nodes / {args.edges} edges power-law graph {'in total' if strong else 'per GPU'}, "
+            "fp64, eps 1e-9, d 0.75")
+
+
+def scoring_workload(args):
+    return (f"BASELINE.json configs[2]: batched cosine scoring, {args.queries} keyword queries over "
+            f"{args.docs}-doc/GPU / {args.terms}-term synthetic Zipf index, PageRank blend + top-{TOP_K}")
+
+
+CACHE_NOTE = ("inputs larger than L2, no flush between steps: per GPU the PageRank state and graph exceed 1 GB and the "
+              "index 8 GB at the default sizes, L2 is 126 MB (exact sizes in `details`)")
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -365,22 +380,22 @@ def run_pagerank(args, ctx):
         "metric": "pagerank_gteps_per_iter", "value": gteps, "unit": "GTEPS (topic-edges/s, E*T per sweep)",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": ("BASELINE.json configs[1]: topic-sensitive PageRank, 16 ODP topics, "
-                                f"{args.nodes} nodes / {args.edges} edges power-law graph "
-                                f"{'in total' if strong else 'per GPU'}, fp64, eps 1e-9, d 0.75"),
-                   "nodes": n_nodes, "edges": E, "topics": T_TOPICS, "sweeps_per_step": sweeps_total / args.steps,
-                   "cache": "inputs larger than L2 (state 2x%.2f GB + graph %.2f GB vs 126 MB L2)" %
-                            (n_nodes * t_g * 8 / 1e9, (4 * E_loc + 8 * R) / 1e9),
-                   "partition": (f"{rg} row groups x {tg} topic groups; rows edge-balanced; sharded export "
-                                 "(ss_graph_load_csr_rows: one all-to-all of the edges at load)") if world > 1
-                                else "single GPU",
-                   "collective": ("per sweep inside a row group: every rank pushes its finished row chunks into the "
-                                  "peers' state with copy-engine peer copies over NVLink (CUDA IPC), overlapped with "
-                                  "the sweep of the next chunk on an exchange stream (SS_PR_EXCHANGE=nccl: grouped "
-                                  "ncclBroadcast instead), + ncclAllReduce of 3*T sums as the barrier" if rg > 2 else
-                                  "2-rank row group: sweep epilogue pushes rows into the peer's state over NVLink "
-                                  "(CUDA IPC peer memory), ncclAllReduce of 3*T sums as the barrier" if rg == 2 else
-                                  "none (topics are independent)")},
+        # `config` is the workload only (the reference arm prints the same dict); how it was run is in `details`
+        "config": {"workload": pagerank_workload(args, strong), "nodes": n_nodes, "edges": E, "topics": T_TOPICS,
+                   "cache": CACHE_NOTE},
+        "details": {"sweeps_per_step": sweeps_total / args.steps,
+                    "cache": "inputs larger than L2 (state 2x%.2f GB + graph %.2f GB vs 126 MB L2)" %
+                             (n_nodes * t_g * 8 / 1e9, (4 * E_loc + 8 * R) / 1e9),
+                    "partition": (f"{rg} row groups x {tg} topic groups; rows edge-balanced; sharded export "
+                                  "(ss_graph_load_csr_rows: one all-to-all of the edges at load)") if world > 1
+                                 else "single GPU",
+                    "collective": ("per sweep inside a row group: every rank pushes its finished row chunks into the "
+                                   "peers' state with copy-engine peer copies over NVLink (CUDA IPC), overlapped with "
+                                   "the sweep of the next chunk on an exchange stream (SS_PR_EXCHANGE=nccl: grouped "
+                                   "ncclBroadcast instead), + ncclAllReduce of 3*T sums as the barrier" if rg > 2 else
+                                   "2-rank row group: sweep epilogue pushes rows into the peer's state over NVLink "
+                                   "(CUDA IPC peer memory), ncclAllReduce of 3*T sums as the barrier" if rg == 2 else
+                                   "none (topics are independent)")},
         "clocks": clocks,
         "e2e": {"value": e2e_gteps, "unit": "GTEPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3 / e2e_steps, "load_ms": eng.pagerank_stats().load_ms,
@@ -552,15 +567,14 @@ def run_scoring(args, ctx):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 sums of f32 weights",
         "data": "synthetic",
-        "config": {"workload": f"BASELINE.json configs[2]: batched cosine scoring, {Q} keyword queries over "
-                               f"{args.docs}-doc/GPU / {V}-term synthetic Zipf index, PageRank blend + top-{TOP_K}",
-                   "docs": D, "terms": V, "queries": Q, "k": TOP_K,
-                   "postings": int(sum_over_ranks(title.n_postings + body.n_postings)),
-                   "cache": "index %.1f GB larger than L2" % ((title.n_postings + body.n_postings) * 8 / 1e9),
-                   "shard": ("docs, shard-local ids + doc base; every rank scores the whole batch, ncclAllGather of the "
-                             "[Q][k] lists + k-way merge on the engine stream inside the timed region "
-                             "(ss_score_batch_sharded)") if world > 1 else "single GPU",
-                   "index_load_s": load_s},
+        "config": {"workload": scoring_workload(args), "docs": D, "terms": V, "queries": Q, "k": TOP_K,
+                   "cache": CACHE_NOTE},
+        "details": {"postings": int(sum_over_ranks(title.n_postings + body.n_postings)),
+                    "cache": "index %.1f GB larger than L2" % ((title.n_postings + body.n_postings) * 8 / 1e9),
+                    "shard": ("docs, shard-local ids + doc base; every rank scores the whole batch, ncclAllGather of the "
+                              "[Q][k] lists + k-way merge on the engine stream inside the timed region "
+                              "(ss_score_batch_sharded)") if world > 1 else "single GPU",
+                    "index_load_s": load_s},
         "clocks": a["clocks"],
         "e2e": {"value": Q * args.steps / a["wall_s"], "unit": "queries/s", "h2d_bytes_per_step": a["h2d"],
                 "d2h_bytes_per_step": a["d2h"], "ms_per_step": a["wall_s"] * 1e3 / args.steps,
@@ -712,8 +726,10 @@ def run_reference(args):
                     "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3 / args.steps,
                     "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                     "data": "synthetic",
-                    "config": {"workload": "BASELINE.json configs[1] on the host CPU (oracle port of ranking/pagerank.go)",
-                               "nodes": args.nodes, "edges": E, "topics": T_TOPICS},
+                    "config": {"workload": pagerank_workload(args), "nodes": args.nodes, "edges": E, "topics": T_TOPICS,
+                               "cache": CACHE_NOTE},
+                    "details": {"what": "the oracle port of ranking/pagerank.go on the host CPU; at N > 1 the "
+                                        "1-GPU size is timed (the CPU rate does not depend on the size)"},
                     "cpu_baseline": {"value": val, "unit": "GTEPS", "cores": cores, "kind": "port", "sample": sample},
                     "e2e": {"value": val, "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                     "gpu_launches": 0})
@@ -734,8 +750,9 @@ def run_reference(args):
               "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs_total * 1e3 / args.steps,
               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 sums of f32 weights",
               "data": "synthetic",
-              "config": {"workload": "BASELINE.json configs[2] on the host CPU (oracle port of retrieval.Retrieve core)",
-                         "docs": D, "terms": V, "queries": args.queries, "k": TOP_K},
+              "config": {"workload": scoring_workload(args), "docs": D, "terms": V, "queries": args.queries, "k": TOP_K,
+                         "cache": CACHE_NOTE},
+              "details": {"what": "the oracle port of the retrieval.Retrieve core on the host CPU"},
               "cpu_baseline": dict(res, value=val),
               "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
               "gpu_launches": 0, "impl": "reference"}
