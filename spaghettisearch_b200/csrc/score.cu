@@ -982,22 +982,73 @@ static int score_batch_entry(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr,
   return SS_OK;
 }
 
+// Very large batches are scored in slices: the per-slab partial lists (n_q * n_slabs * k entries) are capped, and
+// beyond ~250K queries the cap would force slabs wider than the 65536 docs the impact-vector path is built for.
+// BASELINE configs[4] (a 1M-query batch) therefore runs as five slices inside one call; results and statistics
+// are those of the whole batch.
+static uint64_t max_slice() {
+  uint64_t n = 200000;
+  if (const char* env = getenv("SS_SCORE_MAX_SLICE")) n = std::max<uint64_t>(1, strtoull(env, nullptr, 10));
+  return n;
+}
+static int score_batch_sliced(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, const uint32_t* kw_terms,
+                              const uint64_t* ph_ptr, const uint32_t* ph_terms, const double* topic_probs,
+                              int32_t probs_per_query, uint32_t k, uint32_t* out_doc, double* out_final,
+                              double* out_pr, uint32_t* out_count, bool sharded) {
+  const uint64_t kMaxSlice = max_slice();
+  if (n_q <= kMaxSlice || !kw_ptr || !out_doc || !out_final || !out_pr || !out_count || !e)
+    return score_batch_entry(e, n_q, kw_ptr, kw_terms, ph_ptr, ph_terms, topic_probs, probs_per_query, k, out_doc,
+                             out_final, out_pr, out_count, sharded);
+  for (uint64_t q = 0; q < n_q; ++q) {  // the slices rebase the offsets: check them first
+    SS_REQUIRE(kw_ptr[q] <= kw_ptr[q + 1], SS_ERR_INVALID, "ss_score_batch: kw_ptr not monotone at query %llu",
+               (unsigned long long)q);
+    SS_REQUIRE(!ph_ptr || ph_ptr[q] <= ph_ptr[q + 1], SS_ERR_INVALID, "ss_score_batch: ph_ptr not monotone");
+  }
+  ss_score_stats total{};
+  const uint32_t T = e->idx ? e->idx->T : 0;
+  std::vector<uint64_t> s_kw(kMaxSlice + 1), s_ph(kMaxSlice + 1);
+  for (uint64_t lo = 0; lo < n_q; lo += kMaxSlice) {
+    const uint64_t n = std::min(kMaxSlice, n_q - lo);
+    for (uint64_t i = 0; i <= n; ++i) {
+      s_kw[i] = kw_ptr[lo + i] - kw_ptr[lo];
+      if (ph_ptr) s_ph[i] = ph_ptr[lo + i] - ph_ptr[lo];
+    }
+    const double* probs = topic_probs ? (probs_per_query ? topic_probs + lo * T : topic_probs) : nullptr;
+    SS_TRY(score_batch_entry(e, n, s_kw.data(), kw_terms ? kw_terms + kw_ptr[lo] : nullptr, ph_ptr ? s_ph.data() : nullptr,
+                             (ph_ptr && ph_terms) ? ph_terms + ph_ptr[lo] : nullptr, probs, probs_per_query, k,
+                             out_doc + lo * k, out_final + lo * k, out_pr + lo * k, out_count + lo, sharded));
+    std::lock_guard<std::mutex> lock(e->mu);
+    const ss_score_stats& st = e->idx->stats;
+    total.postings_scanned += st.postings_scanned;
+    total.docs_matched += st.docs_matched;
+    total.algorithmic_bytes += st.algorithmic_bytes;
+    total.model_bytes += st.model_bytes;
+    total.launches += st.launches;
+    total.kernel_ms += st.kernel_ms;
+    total.score_kernel_ms += st.score_kernel_ms;
+    total.shard_merge_ms += st.shard_merge_ms;
+  }
+  std::lock_guard<std::mutex> lock(e->mu);
+  e->idx->stats = total;
+  return SS_OK;
+}
+
 extern "C" {
 
 SS_API int ss_score_batch(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, const uint32_t* kw_terms,
                           const uint64_t* ph_ptr, const uint32_t* ph_terms, const double* topic_probs,
                           int32_t probs_per_query, uint32_t k, uint32_t* out_doc, double* out_final, double* out_pr,
                           uint32_t* out_count) {
-  return score_batch_entry(e, n_q, kw_ptr, kw_terms, ph_ptr, ph_terms, topic_probs, probs_per_query, k, out_doc,
-                           out_final, out_pr, out_count, false);
+  return score_batch_sliced(e, n_q, kw_ptr, kw_terms, ph_ptr, ph_terms, topic_probs, probs_per_query, k, out_doc,
+                            out_final, out_pr, out_count, false);
 }
 
 SS_API int ss_score_batch_sharded(ss_engine* e, uint64_t n_q, const uint64_t* kw_ptr, const uint32_t* kw_terms,
                                   const uint64_t* ph_ptr, const uint32_t* ph_terms, const double* topic_probs,
                                   int32_t probs_per_query, uint32_t k, uint32_t* out_doc, double* out_final,
                                   double* out_pr, uint32_t* out_count) {
-  return score_batch_entry(e, n_q, kw_ptr, kw_terms, ph_ptr, ph_terms, topic_probs, probs_per_query, k, out_doc,
-                           out_final, out_pr, out_count, true);
+  return score_batch_sliced(e, n_q, kw_ptr, kw_terms, ph_ptr, ph_terms, topic_probs, probs_per_query, k, out_doc,
+                            out_final, out_pr, out_count, true);
 }
 
 SS_API int ss_merge_topk(ss_engine* e, uint32_t n_lists, uint64_t n_q, uint32_t k, const uint32_t* docs,

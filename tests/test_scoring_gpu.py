@@ -434,3 +434,24 @@ def test_live_topic_probabilities_extension(engine):
                         q.ph_terms, topic_probs=exp * 1e4, k=10)
     assert_same_results(res, ref)
     assert (res[2] != 0).any()  # the blend really is live
+
+
+def test_large_batches_are_sliced(engine, monkeypatch):
+    """Batches beyond 200K queries run as slices inside one call (BASELINE configs[4] is a 1M-query batch);
+    with the slice size forced down, a 350-query mixed batch returns exactly the unsliced rows and the
+    statistics of the whole batch."""
+    V, D = 300, 3000
+    _small_index(engine, V, D)
+    q = synth.queries(350, V, phrase_fraction=0.3, seed=4)
+    rng = np.random.default_rng(8)
+    pr = rng.random((D, 4)) * 1e-3
+    engine.set_pagerank(pr)
+    probs = rng.random((350, 4))
+    whole = engine.score_batch(q.kw_ptr, q.kw_terms, q.ph_ptr, q.ph_terms, topic_probs=probs, k=10)
+    st_whole = engine.score_stats()
+    monkeypatch.setenv("SS_SCORE_MAX_SLICE", "100")
+    sliced = engine.score_batch(q.kw_ptr, q.kw_terms, q.ph_ptr, q.ph_terms, topic_probs=probs, k=10)
+    st_sliced = engine.score_stats()
+    for a, b in zip(whole, sliced):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert st_sliced.postings_scanned == st_whole.postings_scanned and st_sliced.launches > st_whole.launches
