@@ -202,8 +202,13 @@ def run_ours(args):
     from spaghettisearch_b200 import capi, sharding, synth
 
     rank, local, world = dist_env(args)
-    # stdout carries exactly one JSON line: NCCL's own banner/debug lines go to stderr
+    # stdout carries exactly one JSON line.  NCCL prints its version banner on the stdout of whichever process is
+    # rank 0 of a communicator (with a row x topic grid that is several processes), so for the duration of the run
+    # file descriptor 1 points at stderr; it is restored for the one line rank 0 prints at the end.
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -247,6 +252,9 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     if rank == 0:
         print(json.dumps(out), flush=True)
 
@@ -256,10 +264,8 @@ def make_group_engine(ctx, group_rank, group_size, group_id):
     dist, capi, rank = ctx["dist"], ctx["capi"], ctx["rank"]
     eng = capi.Engine(device=ctx["local"], timing=True)
     if group_size > 1:
-        uid = capi.comm_unique_id() if group_rank == 0 else None
-        ids = [None] * ctx["world"]
-        dist.all_gather_object(ids, uid)
-        eng.comm_init(ids[rank - group_rank], group_rank, group_size)
+        eng.comm_init(ctx["sharding"].share_group_unique_id(capi.comm_unique_id, group_rank, group_size), group_rank,
+                      group_size)
     return eng
 
 
@@ -299,9 +305,7 @@ def run_pagerank(args, ctx):
     rank, local, world, threads, cores = ctx["rank"], ctx["local"], ctx["world"], ctx["threads"], ctx["cores"]
     peak, peak_src, barrier = ctx["peak"], ctx["peak_src"], ctx["barrier"]
     rg, tg = pr_grid(world, args.pr_grid)
-    g_rank, t_group = rank % rg, rank // rg
-    t_g = T_TOPICS // tg
-    t_lo = t_group * t_g
+    g_rank, t_group, t_lo, t_g = sharding.engine_grid(rank, rg, tg, T_TOPICS)
     strong = args.scaling == "strong"
     n_nodes = args.nodes if strong else args.nodes * world
     n_edges_target = args.edges if strong else args.edges * world
@@ -403,6 +407,7 @@ def run_pagerank(args, ctx):
                         "ss_pagerank + this rank's rows to pinned host memory; bytes are per rank"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "frac_of_nominal_8TBps": achieved / 8000.0,
                      "traffic": ncu_traffic("pagerank_sweep_dram_bytes") if world == 1 else None,
                      "peak_source": peak_src, "kernel": "k_sweep_short32 + k_sweep_long (one sweep, one rank)",
                      "algorithmic_bytes_per_sweep": b_pr, "avg_sweep_ms": avg_sweep_s * 1e3,
@@ -582,7 +587,7 @@ def run_scoring(args, ctx):
         "gpu_launches": a["launches"],
         "shard_merge_ms_per_step": a["merge_ms"] / args.steps,
         "roofline": {"bound": "hbm", "achieved": a["model_bytes"] / (score_ms * 1e-3) / 1e9, "peak": peak,
-                     "unit": "GB/s", "frac": model_frac,
+                     "unit": "GB/s", "frac": model_frac, "frac_of_nominal_8TBps": model_frac * peak / 8000.0,
                      "traffic": ncu_traffic("score_dram_bytes") if world == 1 else None, "peak_source": peak_src,
                      "kernel": "k_score",
                      "bytes_model": "what the default path has to move: a query with a dense keyword streams 2 B per "

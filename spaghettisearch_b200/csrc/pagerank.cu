@@ -1082,14 +1082,13 @@ struct PagerankState {
   double damping = 0;
   ss::DevBuf<double> y[2];
   int cur = 0;  // y[cur] holds the latest ranks
-  ss::DevBuf<double> mul, partials, red, stage, sums, tot, init, out_stage[2];
+  ss::DevBuf<double> mul, partials, red, stage, sums, tot, init;
   bool have_result = false;
   // topic-biased teleport (ss_pagerank_set_teleport): weights of this rank's rows, [rows_loc][tele_T] as given
   ss::DevBuf<double> tele_raw, tele_w;  // raw [rows_loc][tele_T]; padded [rows_loc][TP] built per run
   uint32_t tele_T = 0;                  // 0: uniform teleport (the reference)
   ss_pagerank_stats stats{};
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [4]: end of the short-row kernel
-  cudaEvent_t out_ev[2] = {nullptr, nullptr};
   // exchange over peer memory (CUDA IPC): peers' y[0]/y[1] mapped into this process.
   //   fused: the peers are mapped (every rank agreed);  push_from_epilogue: 2 ranks, the sweep epilogue stores
   //   each finished row into the peer's state;  otherwise (3+ ranks) finished row chunks are pushed to every
@@ -1195,8 +1194,6 @@ void pagerank_state_free(PagerankState* s) {
   close_peers(s);
   for (auto& e : s->ev)
     if (e) cudaEventDestroy(e);
-  for (auto& e : s->out_ev)
-    if (e) cudaEventDestroy(e);
   for (auto& e : s->chunk_ev)
     if (e) cudaEventDestroy(e);
   if (s->x_done) cudaEventDestroy(s->x_done);
@@ -1244,7 +1241,6 @@ static int dispatch_shape(Shape sh, F&& f) {
 
 static int create_sync_objects(PagerankState* s) {
   for (auto& ev : s->ev) SS_CUDA(cudaEventCreate(&ev));
-  for (auto& ev : s->out_ev) SS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& ev : s->chunk_ev) SS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   SS_CUDA(cudaEventCreateWithFlags(&s->x_done, cudaEventDisableTiming));
   SS_CUDA(cudaEventCreateWithFlags(&s->red_done, cudaEventDisableTiming));

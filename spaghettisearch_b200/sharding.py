@@ -64,6 +64,25 @@ def share_unique_id(make_id):
     return obj[0]
 
 
+def engine_grid(rank: int, row_groups: int, topic_groups: int, n_topics: int):
+    """Place of a rank in the row x topic grid of PageRank engines: ranks of one topic group are
+    consecutive.  -> (rank inside its row group, topic group, first topic, number of topics)."""
+    assert n_topics % topic_groups == 0
+    per = n_topics // topic_groups
+    return rank % row_groups, rank // row_groups, (rank // row_groups) * per, per
+
+
+def share_group_unique_id(make_id, group_rank: int, group_size: int):
+    """One NCCL unique id per group of `group_size` consecutive ranks: the first rank of every group creates
+    one (ss_comm_unique_id), everybody receives the id of its own group.  Collective over the whole world."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = make_id() if group_rank == 0 else None
+    ids = [None] * world
+    dist.all_gather_object(ids, uid)
+    return ids[rank - group_rank]
+
+
 def gather_result_lists(docs: np.ndarray, finals: np.ndarray, prs: np.ndarray, counts: np.ndarray, device="cpu"):
     """All ranks' [Q][k] lists -> [world][Q][k] on every rank (input of ss_merge_topk)."""
     import torch

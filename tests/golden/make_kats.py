@@ -112,7 +112,85 @@ def kat_sc1():
             "query": query, "result": res}
 
 
+def pagerank_biased(children, nodes, d, eps, n, w):
+    """Extension: the same loop with the teleport term (1-d) * w[k] per node, Tot unchanged."""
+    cur, last = {}, {}
+    it, change = 1, float("inf")
+    while change > eps:
+        cur, last = last, cur
+        for k in nodes:
+            if it > 1:
+                cur[k] = 0.0
+            else:
+                cur[k] = last[k] = 1.0 / n
+        tot = 0.0
+        for p in nodes:
+            kids = children.get(p, [])
+            if not kids:
+                continue
+            x = d * last[p] / len(kids)
+            tot += x
+            for c in kids:
+                cur[c] += x
+        tot += (1 - d) * len(cur)
+        change = 0.0
+        for k in nodes:
+            cur[k] = (cur[k] + (1 - d) * w[k]) / tot
+            change += abs(cur[k] - last[k])
+        it += 1
+    return [cur[k] for k in nodes], it - 1
+
+
+def kat_pr2():
+    # KAT-PR-1's graph, topic 0 teleports to {A, B} only, topic 1 uniformly (weights sum to N = 4 per topic)
+    children = {0: [1, 2], 1: [2], 3: [0]}
+    nodes = [0, 1, 2, 3]
+    w0 = {0: 2.0, 1: 2.0, 2: 0.0, 3: 0.0}
+    w1 = {k: 1.0 for k in nodes}
+    r0, i0 = pagerank_biased(children, nodes, 0.75, 1e-12, 7, w0)
+    r1, i1 = pagerank_biased(children, nodes, 0.75, 1e-12, 9, w1)
+    u1, j1 = pagerank(children, nodes, 0.75, 1e-12, 9)
+    assert r1 == u1 and i1 == j1  # all-ones weights are the reference's loop
+    return {"row_ptr": [0, 2, 3, 3, 4], "col_idx": [1, 2, 2, 0], "damping": 0.75, "eps": 1e-12, "num_pages": [7, 9],
+            "weights": [[w0[k], w1[k]] for k in nodes], "rank": [[r0[k], r1[k]] for k in nodes], "iters": [i0, i1]}
+
+
+def kat_tp1():
+    # Extension (SURVEY 8(f)-3): computeTopicProbs (main_retrieve.go:106-159) with probs starting at 1.
+    # inv[2]: word -> {topic: count}; forw[5] wordCount per topic; 3 topics, 4 words
+    inv2 = {0: {0: 3, 2: 1}, 1: {1: 5}, 2: {0: 2, 1: 2, 2: 2}, 3: {}}
+    word_count = [100.0, 50.0, 40.0]
+    queries = [[0], [0, 2], [1, 3], [3], [], [2, 2], [0, 99]]
+    T = 3
+    out = []
+    for q in queries:
+        row = []
+        for t in range(T):
+            probs, any_ = 1.0, False
+            for word in q:
+                f = inv2.get(word, {}).get(t)
+                if f is None:
+                    continue
+                probs *= (float(f) / word_count[t])
+                any_ = True
+            row.append(probs / float(T) if any_ else 0.0)
+        out.append(row)
+    ptr, ids, freq = [0], [], []
+    for word in range(4):
+        for t in sorted(inv2[word]):
+            ids.append(t)
+            freq.append(float(inv2[word][t]))
+        ptr.append(len(ids))
+    tok_ptr = [0]
+    toks = []
+    for q in queries:
+        toks += q
+        tok_ptr.append(len(toks))
+    return {"term_ptr": ptr, "topic_ids": ids, "freq": freq, "word_count": word_count, "tok_ptr": tok_ptr,
+            "tok_terms": toks, "probs": out}
+
+
 if __name__ == "__main__":
-    out = {"KAT-PR-1": kat_pr1(), "KAT-SC-1": kat_sc1()}
+    out = {"KAT-PR-1": kat_pr1(), "KAT-SC-1": kat_sc1(), "KAT-PR-2-biased": kat_pr2(), "KAT-TP-1": kat_tp1()}
     Path(__file__).with_name("kats.json").write_text(json.dumps(out, indent=1))
     print(json.dumps(out["KAT-SC-1"]["result"], indent=1))

@@ -203,3 +203,16 @@ def test_score_batch_fair_flavour_is_identical(built):
             assert np.array_equal(a[0], f[0]) and np.array_equal(a[3], f[3])
             assert np.array_equal(a[1].view(np.uint64), f[1].view(np.uint64))
             assert np.array_equal(a[2].view(np.uint64), f[2].view(np.uint64))
+
+
+def test_extension_kats(built):
+    """The two opt-in extensions against the pure-Python restatement in make_kats.py."""
+    k = KATS["KAT-PR-2-biased"]
+    rank, iters = O.pagerank_biased(np.array(k["row_ptr"], np.uint64), np.array(k["col_idx"], np.uint32), k["damping"],
+                                    k["eps"], np.array(k["num_pages"], np.int64), np.array(k["weights"], np.float64),
+                                    n_threads=1)
+    assert iters.tolist() == k["iters"]
+    assert np.abs(rank - np.array(k["rank"])).max() <= 1e-15
+    t = KATS["KAT-TP-1"]
+    probs = O.topic_probs(t["term_ptr"], t["topic_ids"], t["freq"], t["word_count"], t["tok_ptr"], t["tok_terms"])
+    assert probs.tolist() == t["probs"]  # bit exact: same operations in the same order

@@ -53,6 +53,10 @@ def _worker(rank, world, init_file, ret):
         # ---- the unique id travels as bytes
         uid = sharding.share_unique_id(lambda: bytes(range(128)))
         ok_uid = uid == bytes(range(128))
+        # one id per engine group: two groups of one rank each get their own ids, one group of two shares one
+        own = sharding.share_group_unique_id(lambda: bytes([rank]) * 128, 0, 1)
+        both = sharding.share_group_unique_id(lambda: bytes([7]) * 128, rank, 2)
+        ok_uid = ok_uid and own == bytes([rank]) * 128 and both == bytes([7]) * 128
         # ---- doc-sharded scoring + merge
         dlo, dhi = sharding.doc_shard(rank, world, D)
         tabs = []
@@ -99,6 +103,18 @@ def test_two_rank_gloo(built):
         assert len(ret) == world
         for r in range(world):
             assert ret[r] == (True, True, True), (r, ret[r])
+
+
+def test_engine_grid():
+    from spaghettisearch_b200 import sharding
+    # 8 ranks as 4 row groups x 2 topic groups over 16 topics: ranks 0-3 run topics 0-7, ranks 4-7 topics 8-15
+    grid = [sharding.engine_grid(r, 4, 2, 16) for r in range(8)]
+    assert [g[0] for g in grid] == [0, 1, 2, 3, 0, 1, 2, 3]
+    assert [g[1] for g in grid] == [0, 0, 0, 0, 1, 1, 1, 1]
+    assert [g[2:] for g in grid] == [(0, 8)] * 4 + [(8, 8)] * 4
+    assert sharding.engine_grid(0, 1, 1, 16) == (0, 0, 0, 16)
+    covered = sorted(t for g in {gr[1:] for gr in grid} for t in range(g[1], g[1] + g[2]))
+    assert covered == list(range(16))
 
 
 def test_shard_bounds():
