@@ -140,6 +140,30 @@ def test_synthetic_blend_shared_and_per_query(engine, synth_index):
     engine.set_pagerank(None)
 
 
+def test_blend_at_order_one_magnitude(engine, synth_index):
+    """with ranks around 1/D the blend term never changes an order.  Here the PageRank rows are O(1)
+    (and signed), so 0.33 * sqd * 100 is as large as the text scores and decides most of the top 10: the blend
+    bounds of every path (slab maxima, fp16 blend vector, block maxima, global bound) are exercised for real."""
+    s = synth_index
+    rng = np.random.default_rng(31)
+    pr = rng.uniform(-0.5, 1.5, (s["D"], 16))
+    pr[rng.random(s["D"]) < 0.01] *= 40.0          # a few outliers the bounds must not lose
+    q = synth.queries(600, s["V"], phrase_fraction=0.2, seed=47)
+    engine.set_pagerank(pr)
+    try:
+        for probs in (np.full(16, 1.0 / 16), rng.dirichlet(np.ones(16), size=600), -np.full(16, 1.0 / 16)):
+            got = engine.score_batch(q.kw_ptr, q.kw_terms, q.ph_ptr, q.ph_terms, topic_probs=probs, k=10)
+            ref = O.score_batch(s["ot"], s["ob"], s["D"], s["tmag"], s["bmag"], pr, q.kw_ptr, q.kw_terms, q.ph_ptr,
+                                q.ph_terms, topic_probs=probs, k=10)
+            assert_same_results(got, ref)
+        # the blend really reorders: without it the top doc of most queries is a different one
+        plain = engine.score_batch(q.kw_ptr, q.kw_terms, q.ph_ptr, q.ph_terms, k=10)
+        both = (got[3] > 0) & (plain[3] > 0)
+        assert (got[0][both, 0] != plain[0][both, 0]).mean() > 0.5
+    finally:
+        engine.set_pagerank(None)
+
+
 def test_hot_terms_many_ties(engine, synth_index):
     # single hot term: half the docs match, normTF takes few distinct values -> masses of exact ties,
     # so the order is decided by the doc-id rule
