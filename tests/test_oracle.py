@@ -216,3 +216,80 @@ def test_extension_kats(built):
     t = KATS["KAT-TP-1"]
     probs = O.topic_probs(t["term_ptr"], t["topic_ids"], t["freq"], t["word_count"], t["tok_ptr"], t["tok_terms"])
     assert probs.tolist() == t["probs"]  # bit exact: same operations in the same order
+
+
+def _random_go_tables(rng, n_docs, n_terms):
+    """Two inverted tables in Go shape ({term: {doc: [w, pos...]}}) + the equivalent CSR arrays (weights are
+    final tf-idf weights here: the scorer never looks at how they were made)."""
+    docs = [f"{i:04d}" for i in range(n_docs)]     # ascending string order == ascending dense id
+    terms = [f"t{i:02d}" for i in range(n_terms)]
+    inv, csr = [], []
+    for tb in range(2):
+        table, ptr, ids, w, pp, pos = {}, [0], [], [], [0], []
+        for t in range(n_terms):
+            row = {}
+            for d in sorted(rng.choice(n_docs, size=int(rng.integers(0, n_docs // 2)), replace=False)):
+                weight = np.float32(rng.choice([0.25, 0.5, 1.0, 1.5, 3.0]))
+                kind = rng.integers(0, 4)
+                if kind == 0:
+                    p = []                                         # posting without positions
+                elif kind == 1:
+                    p = [-100.0]                                   # meta/anchor sentinel (parser.go:195-207)
+                else:
+                    p = sorted(float(x) for x in rng.choice(12, size=int(rng.integers(1, 4)), replace=False))
+                row[docs[d]] = [float(weight)] + p
+                ids.append(d); w.append(weight); pos.extend(p); pp.append(len(pos))
+            if row:
+                table[terms[t]] = row
+            ptr.append(len(ids))
+        inv.append(table)
+        csr.append(O.Table(np.array(ptr, np.uint64), np.array(ids, np.uint32), np.array(w, np.float32),
+                           np.array(pp, np.uint64), np.array(pos, np.float32)))
+    return docs, terms, inv, csr
+
+
+def test_oracle_matches_literal_go_translation(built):
+    """The oracle against tests/golden/go_literal.py -- a statement-by-statement Python translation of
+    getFromInverted, getPosTerm, evalPhraseOccurrence, intersect, genAggrDocsPipeline, computeFinalRank and
+    appendSort on Go-shaped maps -- over random small indexes: keyword duplicates, unknown terms, one- to
+    four-word phrases with repeated words, postings without positions, the -100 sentinel, zero norms, blend."""
+    from tests.golden import go_literal as G
+    rng = np.random.default_rng(123)
+    n_checked = n_phrase_hits = 0
+    for trial in range(6):
+        n_docs, n_terms = 40, 10
+        docs, terms, inv, (ot, ob) = _random_go_tables(rng, n_docs, n_terms)
+        tmag = rng.choice([0.0, 0.5, 1.0, 2.0, 7.5], size=n_docs)
+        bmag = rng.choice([0.0, 1.0, 3.0, 4.25], size=n_docs)
+        mag = {docs[d]: {"title": float(tmag[d]), "body": float(bmag[d])} for d in range(n_docs)}
+        T = 3
+        pr = rng.random((n_docs, T))
+        topics = [f"c{t}" for t in range(T)]
+        pr_map = {docs[d]: {topics[t]: float(pr[d, t]) for t in range(T)} for d in range(n_docs)}
+        for use_blend in (False, True):
+            probs = rng.random(T) if use_blend else None
+            kws, phs = [], []
+            for _ in range(60):
+                kws.append([int(x) for x in rng.integers(0, n_terms + 1, size=int(rng.integers(0, 4)))])  # n_terms = unknown
+                phs.append([int(x) for x in rng.integers(0, n_terms, size=int(rng.integers(0, 5)))])
+            kw_ptr = np.zeros(len(kws) + 1, np.uint64); kw_ptr[1:] = np.cumsum([len(x) for x in kws])
+            ph_ptr = np.zeros(len(phs) + 1, np.uint64); ph_ptr[1:] = np.cumsum([len(x) for x in phs])
+            kw = np.array([t if t < n_terms else 0xFFFFFFFF for x in kws for t in x], np.uint32)
+            ph = np.array([t for x in phs for t in x], np.uint32)
+            d, f, p, c = O.score_batch(ot, ob, n_docs, tmag, bmag, pr if use_blend else None, kw_ptr, kw, ph_ptr, ph,
+                                       topic_probs=probs, k=50)
+            for qi in range(len(kws)):
+                name = lambda t: terms[t] if t < n_terms else "unknown"
+                lit = G.retrieve([name(t) for t in kws[qi]], [name(t) for t in phs[qi]], inv, mag, pr_map,
+                                 {topics[t]: float(probs[t]) for t in range(T)} if use_blend else None)
+                # the literal code keeps NaN/inf as Go would; the oracle's order puts NaN last: skip those queries
+                if any(math.isnan(x[1]) for x in lit):
+                    continue
+                got = [(docs[d[qi, j]], f[qi, j], p[qi, j]) for j in range(int(c[qi]))]
+                assert [g[0] for g in got] == [x[0] for x in lit], (trial, qi, kws[qi], phs[qi])
+                assert [g[1] for g in got] == [x[1] for x in lit], (trial, qi)     # bit exact: same operations
+                assert [g[2] for g in got] == [x[2] for x in lit], (trial, qi)
+                n_checked += 1
+                if phs[qi] and G.get_phrase_from_inverted([name(t) for t in phs[qi]], inv):
+                    n_phrase_hits += 1
+    assert n_checked > 600 and n_phrase_hits > 50
