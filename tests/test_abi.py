@@ -43,3 +43,23 @@ def test_fails_loudly_without_gpu(gpu_lib):
     with pytest.raises(capi.SSError) as ei:
         capi.Engine()
     assert ei.value.code == -6 and "no CPU path" in str(ei.value)
+
+
+def test_header_is_c99_and_links_from_c(gpu_lib, tmp_path):
+    """cgo compiles include/spaghetti.h as C: a C99 translation unit that takes the address of every entry point
+    must compile with -pedantic -Werror, link against the library and behave (no device here => loud failure)."""
+    import subprocess
+    from spaghettisearch_b200 import _build
+    exe = tmp_path / "c_abi_check"
+    src = ROOT / "tests" / "c_abi_check.c"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I",
+                    str(ROOT / "include"), "-o", str(exe), str(src), "-L", str(_build.PKG), "-lspaghetti_gpu",
+                    f"-Wl,-rpath,{_build.PKG}"], check=True, capture_output=True, text=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "entry points" in r.stdout
+    # every SS_API declaration of the header is referenced by the C file
+    header = (ROOT / "include" / "spaghetti.h").read_text()
+    declared = set(re.findall(r"SS_API\s+[\w\s\*]+?\b(ss_\w+)\s*\(", header))
+    used = set(re.findall(r"\(fn_t\)(ss_\w+)", src.read_text()))
+    assert declared == used, declared ^ used
