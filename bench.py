@@ -206,9 +206,11 @@ def run_ours(args):
     # rank 0 of a communicator (with a row x topic grid that is several processes), so for the duration of the run
     # file descriptor 1 points at stderr; it is restored for the one line rank 0 prints at the end.
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    sys.stdout.flush()
-    saved_stdout = os.dup(1)
-    os.dup2(2, 1)
+    saved_stdout = None
+    if world > 1:  # a single process creates no communicator: nothing to keep off stdout
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -252,9 +254,10 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    sys.stdout.flush()
-    os.dup2(saved_stdout, 1)
-    os.close(saved_stdout)
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     if rank == 0:
         print(json.dumps(out), flush=True)
 
