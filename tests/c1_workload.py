@@ -78,10 +78,12 @@ def run(engine, tmp_path, w, eps=1e-9):
         # exports and uploads the whole index for every query
         t0 = time.perf_counter()
         results, n_calls, n_served = db.retrieve_concurrent(engine, qs, threads=8, window_us=200)
-        times["Retrieve x%d" % len(qs)] = time.perf_counter() - t0
+        times["Retrieve x%d" % len(qs)] = time.perf_counter() - t0  # includes building the resident index once
         times["score_batch_calls"] = n_calls
         assert n_served == len(qs)
+        t0 = time.perf_counter()
         cold = db.retrieve(engine, qs[0][0], qs[0][1])  # one cold call: same rows as the served one
+        times["cold Retrieve x1 (exports the index again)"] = time.perf_counter() - t0
         assert cold == results[0]
         for t in ("forw3", "forw4"):
             db.save(t, tmp_path / f"{t}.out.jsonl")
